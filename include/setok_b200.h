@@ -1,0 +1,186 @@
+/* setok_b200.h — C ABI of the B200-native SeTok tokenizer hot path (libsetok_b200.so).
+ *
+ * Plain pointers and sizes only; no torch types.  Every pointer marked (device) is a CUDA device
+ * pointer owned by the caller; buffers are row-major and contiguous unless a leading dimension is
+ * passed.  No entry point allocates, synchronises or throws: each enqueues work on `stream` and
+ * returns SETOK_OK (0) or a negative setok_status; setok_last_error() gives the message of the last
+ * failure on the calling thread.  Distinct streams may be driven from distinct threads.
+ *
+ * The reference (ChocoWu/SeTok) is pure Python and has no FFI; the seam these entry points sit
+ * behind is the duck-typed Python plugin API.  Each entry cites the reference
+ * code it replaces (paths relative to the reference root).  INTEGRATION.md shows the ctypes
+ * binding a reference maintainer would add.
+ */
+#ifndef SETOK_B200_H_
+#define SETOK_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* setok_stream_t; /* cudaStream_t */
+
+typedef enum {
+  SETOK_OK = 0,
+  SETOK_ERR_BAD_ARG = -1,      /* null pointer, non-positive size, misaligned buffer            */
+  SETOK_ERR_UNSUPPORTED = -2,  /* shape outside what the sm_100a kernels are instantiated for   */
+  SETOK_ERR_CUDA = -3,         /* a CUDA runtime / driver call failed (message has the reason)   */
+  SETOK_ERR_WORKSPACE = -4     /* workspace smaller than the matching *_workspace_bytes() query  */
+} setok_status;
+
+typedef enum { SETOK_F32 = 0, SETOK_BF16 = 1 } setok_dtype;
+typedef enum { SETOK_ACT_NONE = 0, SETOK_ACT_QUICK_GELU = 1, SETOK_ACT_GELU_ERF = 2 } setok_act;
+
+const char* setok_last_error(void);
+int setok_abi_version(void);
+/* Number of kernels this library has launched since load (process-wide, all streams). */
+uint64_t setok_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Primitive: D[M,N] = epilogue(A[M,K] * W[N,K]^T)  — tcgen05/TMEM/TMA GEMM, bf16 in, fp32 accumulate.
+ * Replaces every nn.Linear on the path (HF CLIP q/k/v/out_proj/fc1/fc2, src/model/setok/module.py:34-36,
+ * :56-58, src/model/setok/tokenizer.py:43, src/model/multimodal_projector/builder.py:37,50-58).
+ *   A, W        (device) bf16, leading dimensions lda/ldw in elements (multiples of 8, 16-byte aligned)
+ *   D           (device) bf16 or f32 (out_dtype), leading dimension ldd
+ *   bias        (device) f32 [N] or NULL
+ *   residual    (device) bf16/f32 (residual_dtype) [M, ldr] or NULL; added after the activation
+ *   m_dev       (device) optional int32: the live row count (rows >= *m_dev are skipped); M is then the
+ *               capacity the buffers were sized for.  This is how ragged (data-dependent K) batches run
+ *               without a host sync.
+ *   K % 8 == 0, N % 8 == 0.
+ */
+int setok_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* D, int64_t ldd,
+                    int out_dtype, const float* bias, const void* residual, int64_t ldr, int residual_dtype,
+                    int act, int M, int N, int K, const int32_t* m_dev, setok_stream_t stream);
+
+/* Row LayerNorm (eps inside the sqrt, biased variance — torch.nn.LayerNorm).  in/out dtype f32|bf16.
+ * gather (device, int32 [rows]) optionally picks the source row: out[r] = LN(in[gather[r]]). */
+int setok_layernorm(const void* in, int in_dtype, void* out, int out_dtype, const float* gamma, const float* beta,
+                    float eps, int rows, int C, const int32_t* gather, const int32_t* m_dev, setok_stream_t stream);
+
+/* Segmented (block-diagonal / varlen) multi-head self-attention over packed rows.
+ * qkv bf16 [rows, 3C] laid out [q | k | v], heads of C/heads; row r attends to rows
+ * [seg_off[s], seg_off[s+1]) where s = row_seg[r].  softmax(q k^T * scale) v, fp32 math.
+ * Replaces Attention.forward (src/model/setok/module.py:61-73) for the per-cluster encoder
+ * (tokenizer.py:150, segments = clusters) and the inter-cluster encoder (tokenizer.py:179, segments =
+ * images), and the HF CLIP attention when uniform_T > 0 (segments = images of uniform_T rows,
+ * seg_off/row_seg may then be NULL). */
+int setok_attention(const void* qkv, void* out, int rows, int C, int heads, float scale,
+                    const int32_t* seg_off, const int32_t* row_seg, int uniform_T, const int32_t* m_dev,
+                    setok_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a1+a2: vision tower.  Replaces CLIPVisionTower.forward + feature_select
+ * (src/model/setok/clip_encoder.py:50-62, :40-48) and the HF CLIPVisionTransformer it calls
+ * (transformers/models/clip/modeling_clip.py:138-220, 261-386, 647-690).
+ */
+typedef struct {
+  const void* w_qkv;   /* bf16 [3C, C]  rows = q_proj | k_proj | v_proj */
+  const float* b_qkv;  /* f32 [3C] */
+  const void* w_o;     /* bf16 [C, C] */
+  const float* b_o;
+  const void* w_fc1;   /* bf16 [F, C] */
+  const float* b_fc1;
+  const void* w_fc2;   /* bf16 [C, F] */
+  const float* b_fc2;
+  const float* ln1_g; const float* ln1_b; const float* ln2_g; const float* ln2_b;
+} setok_vit_layer;
+
+typedef struct {
+  int image_size, patch, hidden, heads, layers, mlp;
+  float ln_eps;
+  const void* w_patch;   /* bf16 [C, Kp], Kp = round_up(3*patch*patch, 64), columns (c, ky, kx), zero padded */
+  const float* cls;      /* f32 [C] */
+  const float* pos;      /* f32 [(N+1), C] */
+  const float* pre_ln_g; const float* pre_ln_b;
+  const setok_vit_layer* layer;   /* host array of `layers` entries */
+} setok_vit;
+
+size_t setok_vit_workspace_bytes(const setok_vit* vit, int B);
+/* images (device) [B,3,H,W] f32|bf16 -> features (device) [B, N(+1), C] f32|bf16.
+ * n_layers_run = index into HF hidden_states (select_layer resolved by the caller: -2 -> layers-1).
+ * keep_cls: 0 = 'patch' (drop CLS), 1 = 'cls_patch'. */
+int setok_vit_forward(const setok_vit* vit, const void* images, int image_dtype, int B, int n_layers_run,
+                      int keep_cls, void* features, int feature_dtype, void* workspace, size_t workspace_bytes,
+                      setok_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a3+a4: 2-D sincos position embedding add + DPC-kNN clustering.  Replaces PositionalEncoding2D
+ * (src/model/setok/module.py:105-146, utils.py:5-10), the add at tokenizer.py:164-169 and
+ * SetokTokenizer.cluster_dpc_knn (tokenizer.py:78-121).
+ *   feats       (device) [B, N, C] f32|bf16, N = h*w
+ *   noise       (device) f32 [B, N]: the U[0,1) draw of tokenizer.py:91 (scaled by 1e-6 inside)
+ *   token_mask  (device) f32 [B, N] or NULL (tokenizer.py:84-86, 93-94; >0 keeps the token)
+ *   x_pos       (device) f32 [B, N, C] out: feats + pos  (the tensor tokenizer.py:168 produces)
+ *   idx_cluster (device) int64 [B, N] out;  score f32 [B, N] out
+ *   index_down  (device) int64 [B, N] out: first num_clusters[b] entries valid, rest -1
+ *   num_clusters(device) int32 [B] out;  offsets int32 [B+1] out (exclusive scan of num_clusters)
+ */
+size_t setok_dpc_workspace_bytes(int B, int N, int C);
+int setok_dpc_cluster(const void* feats, int feat_dtype, const float* noise, const float* token_mask,
+                      int B, int h, int w, int C, int k, float threshold, int min_cluster_num,
+                      float* x_pos, int64_t* idx_cluster, float* score, int64_t* index_down,
+                      int32_t* num_clusters, int32_t* offsets, void* workspace, size_t workspace_bytes,
+                      setok_stream_t stream);
+/* Same, with the (h*w, C) f32 sincos table supplied by the caller (device).  The Python host passes the
+ * table torch computes with the reference's own formula, so x_pos is bit-identical to the reference's;
+ * setok_dpc_cluster() builds the table itself (libm, cached per (device, h, w, C)). */
+int setok_dpc_cluster_pos(const void* feats, int feat_dtype, const float* pos_table, const float* noise,
+                          const float* token_mask, int B, int h, int w, int C, int k, float threshold,
+                          int min_cluster_num, float* x_pos, int64_t* idx_cluster, float* score,
+                          int64_t* index_down, int32_t* num_clusters, int32_t* offsets, void* workspace,
+                          size_t workspace_bytes, setok_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a5+a6: group_encoding (tokenizer.py:123-155) + inter_encoder + out (tokenizer.py:179-180) with
+ * Block/Attention/Mlp (module.py:29-100).  Consumes the clustering outputs, emits the ragged batch
+ * packed as tokens [sum K, C_tok] + offsets (from setok_dpc_cluster).
+ */
+typedef struct { const void* w_qkv; const float* b_qkv; const void* w_proj; const float* b_proj; } setok_attn;
+typedef struct {
+  int depth;                     /* number of attention layers sharing norm1 (module.py:86-91) */
+  const float* n1_g; const float* n1_b; const float* n2_g; const float* n2_b;
+  const setok_attn* attn;        /* host array [depth] */
+  const void* w_fc1; const float* b_fc1;   /* bf16 [F, C] */
+  const void* w_fc2; const float* b_fc2;   /* bf16 [C, F] */
+} setok_block;
+
+typedef struct {
+  int hidden, heads, mlp, token_dim;
+  setok_block inner, inter;
+  const void* w_out; const float* b_out;   /* bf16 [C_tok, C] */
+} setok_head;
+
+size_t setok_head_workspace_bytes(const setok_head* head, int B, int N);
+/* tokens (device) [B*N (capacity), C_tok] f32|bf16 out: rows [offsets[b], offsets[b+1]) are image b's tokens.
+ * group_features (device) f32 [B*N, C] optional out (NULL to skip): the (K, C) tensor of tokenizer.py:153. */
+int setok_head_forward(const setok_head* head, const float* x_pos, const int64_t* idx_cluster,
+                       const int32_t* num_clusters, const int32_t* offsets, int B, int N,
+                       void* tokens, int token_dtype, float* group_features,
+                       void* workspace, size_t workspace_bytes, setok_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a8: mm_in_projector (src/model/multimodal_projector/builder.py:33-64) applied to the packed rows
+ * (src/model/setokim_arch.py:210).  n_linear Linear layers with GELU(erf) between them; optional
+ * LayerNorm after the first ('_Norm').
+ */
+typedef struct {
+  int n_linear;
+  const void* const* w;      /* host array of bf16 [out_i, in_i] */
+  const float* const* b;     /* host array of f32 [out_i] */
+  const int* dims;           /* host array [n_linear + 1]: in_0, out_0 (= in_1), ... */
+  const float* norm_g; const float* norm_b;   /* NULL unless '_Norm' */
+} setok_projector;
+
+size_t setok_project_workspace_bytes(const setok_projector* proj, int rows);
+int setok_project(const setok_projector* proj, const void* tokens, int token_dtype, int rows_capacity,
+                  const int32_t* m_dev, void* out, int out_dtype, void* workspace, size_t workspace_bytes,
+                  setok_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SETOK_B200_H_ */

@@ -110,11 +110,12 @@ def dpc_margins(x: torch.Tensor, k: int, noise: torch.Tensor, threshold: float, 
     if sel.shape[0] > 1:
         two = torch.topk(sel, 2, dim=0, largest=False).values
         gap = two[1] - two[0]
-        keep = torch.ones_like(gap, dtype=torch.bool)
-        keep[index_down] = False           # centres are overwritten (:117-119): no decision there
-        out["argmin_margin"] = float(gap[keep].min()) if bool(keep.any()) else float("inf")
+        gap[index_down] = float("inf")     # centres are overwritten (:117-119): no decision there
+        out["argmin_margin"] = float(gap.min())
     else:
+        gap = torch.full((x.shape[0],), float("inf"))
         out["argmin_margin"] = float("inf")
+    out["token_gap"] = gap                 # per-token gap between the two nearest centres
     return out
 
 
@@ -405,3 +406,20 @@ def mog_features(N: int, C: int, G: int, sigma: float = 0.05, seed: int = 0) -> 
 def tie_noise(N: int, seed: int) -> torch.Tensor:
     """R3: the explicit stand-in for `torch.rand(density.shape)` at tokenizer.py:91."""
     return torch.rand(N, generator=torch.Generator().manual_seed(seed))
+
+
+def well_posed_features(N: int, C: int, G: int, k: int, min_cluster_num: int, threshold: float = 0.5, seed0: int = 0,
+                        min_margin: float = 2e-4, tries: int = 60):
+    """Test helper: seeded (features, noise) for one image whose every integer decision in `dpc_knn` (after the
+    position embedding is added) has a margin above `min_margin`, so that an implementation with a different
+    but equally valid fp32 summation order must reproduce the integers exactly."""
+    h = int(math.sqrt(N))
+    pos = pos_encoding_2d(h, h, C).reshape(N, C)
+    for t in range(tries):
+        seed = seed0 + t
+        f = mog_features(N, C, G, 0.05, seed) if G else torch.randn(N, C, generator=torch.Generator().manual_seed(seed))
+        noise = tie_noise(N, seed + 5000)
+        m = dpc_margins(f + pos, k, noise, threshold, min_cluster_num)
+        if m["threshold_margin"] > min_margin and m["argmin_margin"] > min_margin:
+            return f, noise
+    raise RuntimeError("no well-posed seed found")

@@ -1,0 +1,11 @@
+"""setok_b200 — B200-native SeTok vision tokenizer hot path.
+
+Importing the package does not need a GPU; running anything does, and needs libsetok_b200.so
+(`python -m setok_b200.build`).  There is no CPU fallback."""
+from ._lib import SetokError  # noqa: F401
+from .builder import build_vision_projector, build_vision_tower, encode_images  # noqa: F401
+from .ragged import RaggedTokens  # noqa: F401
+from .tokenizer import CLIPVisionTower, SetokTokenizer  # noqa: F401
+
+__all__ = ["SetokTokenizer", "CLIPVisionTower", "RaggedTokens", "build_vision_tower", "build_vision_projector",
+           "encode_images", "SetokError"]

@@ -1,0 +1,108 @@
+"""ctypes binding of libsetok_b200.so (the C ABI declared in include/setok_b200.h).
+
+There is no fallback: if the shared library is missing or a call fails, a `SetokError` is raised.
+Build it with `python -m setok_b200.build` (or `__graft_entry__.build()`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsetok_b200.so")
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_QUICK_GELU, ACT_GELU_ERF = 0, 1, 2
+
+c_void_p, c_int, c_float, c_size_t, c_int64 = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_int64
+
+
+class SetokError(RuntimeError):
+    pass
+
+
+class VitLayer(C.Structure):
+    _fields_ = [(n, c_void_p) for n in ("w_qkv", "b_qkv", "w_o", "b_o", "w_fc1", "b_fc1", "w_fc2", "b_fc2",
+                                        "ln1_g", "ln1_b", "ln2_g", "ln2_b")]
+
+
+class Vit(C.Structure):
+    _fields_ = [("image_size", c_int), ("patch", c_int), ("hidden", c_int), ("heads", c_int), ("layers", c_int),
+                ("mlp", c_int), ("ln_eps", c_float), ("w_patch", c_void_p), ("cls", c_void_p), ("pos", c_void_p),
+                ("pre_ln_g", c_void_p), ("pre_ln_b", c_void_p), ("layer", C.POINTER(VitLayer))]
+
+
+class Attn(C.Structure):
+    _fields_ = [(n, c_void_p) for n in ("w_qkv", "b_qkv", "w_proj", "b_proj")]
+
+
+class Block(C.Structure):
+    _fields_ = [("depth", c_int), ("n1_g", c_void_p), ("n1_b", c_void_p), ("n2_g", c_void_p), ("n2_b", c_void_p),
+                ("attn", C.POINTER(Attn)), ("w_fc1", c_void_p), ("b_fc1", c_void_p), ("w_fc2", c_void_p), ("b_fc2", c_void_p)]
+
+
+class Head(C.Structure):
+    _fields_ = [("hidden", c_int), ("heads", c_int), ("mlp", c_int), ("token_dim", c_int), ("inner", Block),
+                ("inter", Block), ("w_out", c_void_p), ("b_out", c_void_p)]
+
+
+class Projector(C.Structure):
+    _fields_ = [("n_linear", c_int), ("w", C.POINTER(c_void_p)), ("b", C.POINTER(c_void_p)), ("dims", C.POINTER(c_int)),
+                ("norm_g", c_void_p), ("norm_b", c_void_p)]
+
+
+# name -> (restype, argtypes); every symbol include/setok_b200.h declares
+SIGNATURES = {
+    "setok_last_error": (C.c_char_p, []),
+    "setok_abi_version": (c_int, []),
+    "setok_launch_count": (C.c_uint64, []),
+    "setok_gemm_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64,
+                                c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "setok_layernorm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p,
+                                c_void_p, c_void_p]),
+    "setok_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "setok_vit_workspace_bytes": (c_size_t, [C.POINTER(Vit), c_int]),
+    "setok_vit_forward": (c_int, [C.POINTER(Vit), c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    "setok_dpc_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "setok_dpc_cluster": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "setok_dpc_cluster_pos": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
+                                      c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "setok_head_workspace_bytes": (c_size_t, [C.POINTER(Head), c_int, c_int]),
+    "setok_head_forward": (c_int, [C.POINTER(Head), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
+                                   c_void_p, c_void_p, c_size_t, c_void_p]),
+    "setok_project_workspace_bytes": (c_size_t, [C.POINTER(Projector), c_int]),
+    "setok_project": (c_int, [C.POINTER(Projector), c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Loads the library (once).  Raises SetokError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SetokError(f"{LIB_PATH} not found: build the CUDA library first (python -m setok_b200.build). "
+                         "setok_b200 has no CPU or PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise SetokError(f"{LIB_PATH} does not export {name}; stale build?") from e
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = load().setok_last_error().decode("utf-8", "replace")
+        raise SetokError(f"{what} failed with status {status}: {msg}")
+
+
+def launch_count() -> int:
+    return int(load().setok_launch_count())

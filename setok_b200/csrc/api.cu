@@ -1,0 +1,241 @@
+// api.cu — host-side orchestration behind the C ABI: the vision tower, the clustering head encoders and
+// the projector are each one call that enqueues its whole kernel sequence on the caller's stream.
+// No allocation, no synchronisation: scratch comes from the caller's workspace, ragged row counts stay
+// on the device (offsets[B] is read by the kernels themselves).
+#include "common.cuh"
+#include "rowops.cuh"
+
+#include <cmath>
+
+using namespace setok;
+
+namespace {
+
+struct VitBufs { bf16* A; float* emb; bf16 *x, *h, *qkv, *ao, *u; };
+
+int vit_carve(const setok_vit* v, int B, Arena& a, VitBufs* o) {
+  const int P = (v->image_size / v->patch) * (v->image_size / v->patch);
+  const int T = P + 1, C = v->hidden;
+  const int Kp = static_cast<int>(round_up(3 * v->patch * v->patch, 64));
+  const size_t R = static_cast<size_t>(B) * T;
+  o->A = a.take<bf16>(static_cast<size_t>(B) * P * Kp);
+  o->emb = a.take<float>(R * C);
+  o->x = a.take<bf16>(R * C);
+  o->h = a.take<bf16>(R * C);
+  o->qkv = a.take<bf16>(R * 3 * C);
+  o->ao = a.take<bf16>(R * C);
+  o->u = a.take<bf16>(R * v->mlp);
+  return SETOK_OK;
+}
+
+int check_vit(const setok_vit* v) {
+  SETOK_REQUIRE(v != nullptr, SETOK_ERR_BAD_ARG, "vit: null config");
+  SETOK_REQUIRE(v->image_size > 0 && v->patch > 0 && v->image_size % v->patch == 0, SETOK_ERR_BAD_ARG,
+                "vit: image_size %d not a multiple of patch %d", v->image_size, v->patch);
+  SETOK_REQUIRE(v->hidden > 0 && v->heads > 0 && v->hidden % v->heads == 0 && v->hidden % 8 == 0, SETOK_ERR_UNSUPPORTED,
+                "vit: hidden %d / heads %d unsupported", v->hidden, v->heads);
+  SETOK_REQUIRE(v->mlp > 0 && v->mlp % 8 == 0 && v->layers >= 0, SETOK_ERR_UNSUPPORTED, "vit: mlp %d layers %d unsupported", v->mlp, v->layers);
+  SETOK_REQUIRE(v->w_patch && v->cls && v->pos && v->pre_ln_g && v->pre_ln_b && (v->layers == 0 || v->layer), SETOK_ERR_BAD_ARG, "vit: null weights");
+  return SETOK_OK;
+}
+
+struct BlockBufs { bf16 *h, *qkv, *ao, *u; };
+
+// Block.forward (reference module.py:95-100): depth x [x += Attn_i(norm1(x))], then x += Mlp(norm2(x)).
+// x is the fp32 residual stream over packed rows; attention is restricted to each row's segment.
+int run_block(const setok_block& blk, int C, int heads, int F, float* x, int rows_cap, const int32_t* m_dev,
+              const int32_t* seg_off, const int32_t* row_seg, const BlockBufs& w, cudaStream_t stream) {
+  const float scale = 1.0f / std::sqrt(static_cast<float>(C / heads));
+  for (int i = 0; i < blk.depth; ++i) {
+    const setok_attn& at = blk.attn[i];
+    SETOK_TRY(launch_layernorm(x, SETOK_F32, w.h, SETOK_BF16, blk.n1_g, blk.n1_b, 1e-5f, rows_cap, C, nullptr, m_dev, stream));
+    SETOK_TRY(launch_gemm(GemmArgs{w.h, C, at.w_qkv, C, w.qkv, 3LL * C, SETOK_BF16, at.b_qkv, nullptr, 0, 0, SETOK_ACT_NONE, rows_cap, 3 * C, C, m_dev, 0}, stream));
+    SETOK_TRY(launch_attention(w.qkv, w.ao, rows_cap, C, heads, scale, seg_off, row_seg, 0, m_dev, stream));
+    SETOK_TRY(launch_gemm(GemmArgs{w.ao, C, at.w_proj, C, x, C, SETOK_F32, at.b_proj, x, C, SETOK_F32, SETOK_ACT_NONE, rows_cap, C, C, m_dev, 0}, stream));
+  }
+  SETOK_TRY(launch_layernorm(x, SETOK_F32, w.h, SETOK_BF16, blk.n2_g, blk.n2_b, 1e-5f, rows_cap, C, nullptr, m_dev, stream));
+  SETOK_TRY(launch_gemm(GemmArgs{w.h, C, blk.w_fc1, C, w.u, F, SETOK_BF16, blk.b_fc1, nullptr, 0, 0, SETOK_ACT_GELU_ERF, rows_cap, F, C, m_dev, 0}, stream));
+  SETOK_TRY(launch_gemm(GemmArgs{w.u, F, blk.w_fc2, F, x, C, SETOK_F32, blk.b_fc2, x, C, SETOK_F32, SETOK_ACT_NONE, rows_cap, C, F, m_dev, 0}, stream));
+  return SETOK_OK;
+}
+
+int check_block(const setok_block& b, const char* name) {
+  SETOK_REQUIRE(b.depth >= 0 && (b.depth == 0 || b.attn) && b.n1_g && b.n1_b && b.n2_g && b.n2_b && b.w_fc1 && b.b_fc1 && b.w_fc2 && b.b_fc2,
+                SETOK_ERR_BAD_ARG, "head: null weights in %s block", name);
+  for (int i = 0; i < b.depth; ++i)
+    SETOK_REQUIRE(b.attn[i].w_qkv && b.attn[i].b_qkv && b.attn[i].w_proj && b.attn[i].b_proj, SETOK_ERR_BAD_ARG, "head: null attention weights in %s block layer %d", name, i);
+  return SETOK_OK;
+}
+
+struct HeadBufs { int32_t *perm, *row_seg, *seg_off, *img_seg; float *xs, *g; bf16* gb; BlockBufs bb; };
+
+void head_carve(const setok_head* hd, int B, int N, Arena& a, HeadBufs* o) {
+  const size_t R = static_cast<size_t>(B) * N;
+  const int C = hd->hidden;
+  o->perm = a.take<int32_t>(R);
+  o->row_seg = a.take<int32_t>(R);
+  o->seg_off = a.take<int32_t>(R + 1);
+  o->img_seg = a.take<int32_t>(R);
+  o->xs = a.take<float>(R * C);
+  o->g = a.take<float>(R * C);
+  o->gb = a.take<bf16>(R * C);
+  o->bb.h = a.take<bf16>(R * C);
+  o->bb.qkv = a.take<bf16>(R * 3 * C);
+  o->bb.ao = a.take<bf16>(R * C);
+  o->bb.u = a.take<bf16>(R * hd->mlp);
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" size_t setok_vit_workspace_bytes(const setok_vit* vit, int B) {
+  if (vit == nullptr || B <= 0 || vit->patch <= 0) return 0;
+  Arena a(nullptr, 0);
+  VitBufs b;
+  vit_carve(vit, B, a, &b);
+  return a.off;
+}
+
+extern "C" int setok_vit_forward(const setok_vit* v, const void* images, int image_dtype, int B, int n_layers_run, int keep_cls,
+                                 void* features, int feature_dtype, void* workspace, size_t workspace_bytes, setok_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SETOK_TRY(check_vit(v));
+  SETOK_REQUIRE(images && features && B > 0, SETOK_ERR_BAD_ARG, "vit_forward: null images/features or B <= 0");
+  SETOK_REQUIRE(n_layers_run >= 0 && n_layers_run <= v->layers, SETOK_ERR_BAD_ARG, "vit_forward: n_layers_run %d outside [0, %d]", n_layers_run, v->layers);
+  SETOK_REQUIRE(workspace && workspace_bytes >= setok_vit_workspace_bytes(v, B), SETOK_ERR_WORKSPACE, "vit_forward: workspace too small");
+  const int G = v->image_size / v->patch, P = G * G, T = P + 1, C = v->hidden, F = v->mlp;
+  const int Kp = static_cast<int>(round_up(3 * v->patch * v->patch, 64));
+  const int R = B * T;
+  Arena a(workspace, workspace_bytes);
+  VitBufs w;
+  vit_carve(v, B, a, &w);
+
+  // embeddings (modeling_clip.py:199-220): conv patch-embed as im2col + GEMM whose epilogue scatters the
+  // rows past each image's CLS slot and adds the position embedding; CLS rows; pre_layrnorm.
+  SETOK_TRY(launch_im2col(images, image_dtype, w.A, B, v->image_size, v->image_size, v->patch, Kp, stream));
+  SETOK_TRY(launch_gemm(GemmArgs{w.A, Kp, v->w_patch, Kp, w.emb, C, SETOK_F32, nullptr, v->pos, C, SETOK_F32, SETOK_ACT_NONE, B * P, C, Kp, nullptr, P}, stream));
+  SETOK_TRY(launch_cls_rows(w.emb, v->cls, v->pos, B, T, C, stream));
+  SETOK_TRY(launch_layernorm(w.emb, SETOK_F32, w.x, SETOK_BF16, v->pre_ln_g, v->pre_ln_b, v->ln_eps, R, C, nullptr, nullptr, stream));
+
+  const float scale = 1.0f / std::sqrt(static_cast<float>(C / v->heads));
+  for (int l = 0; l < n_layers_run; ++l) {
+    const setok_vit_layer& L = v->layer[l];
+    SETOK_REQUIRE(L.w_qkv && L.b_qkv && L.w_o && L.b_o && L.w_fc1 && L.b_fc1 && L.w_fc2 && L.b_fc2 && L.ln1_g && L.ln1_b && L.ln2_g && L.ln2_b,
+                  SETOK_ERR_BAD_ARG, "vit_forward: null weights in layer %d", l);
+    // CLIPEncoderLayer.forward (modeling_clip.py:363-386)
+    SETOK_TRY(launch_layernorm(w.x, SETOK_BF16, w.h, SETOK_BF16, L.ln1_g, L.ln1_b, v->ln_eps, R, C, nullptr, nullptr, stream));
+    SETOK_TRY(launch_gemm(GemmArgs{w.h, C, L.w_qkv, C, w.qkv, 3LL * C, SETOK_BF16, L.b_qkv, nullptr, 0, 0, SETOK_ACT_NONE, R, 3 * C, C, nullptr, 0}, stream));
+    SETOK_TRY(launch_attention(w.qkv, w.ao, R, C, v->heads, scale, nullptr, nullptr, T, nullptr, stream));
+    SETOK_TRY(launch_gemm(GemmArgs{w.ao, C, L.w_o, C, w.x, C, SETOK_BF16, L.b_o, w.x, C, SETOK_BF16, SETOK_ACT_NONE, R, C, C, nullptr, 0}, stream));
+    SETOK_TRY(launch_layernorm(w.x, SETOK_BF16, w.h, SETOK_BF16, L.ln2_g, L.ln2_b, v->ln_eps, R, C, nullptr, nullptr, stream));
+    SETOK_TRY(launch_gemm(GemmArgs{w.h, C, L.w_fc1, C, w.u, F, SETOK_BF16, L.b_fc1, nullptr, 0, 0, SETOK_ACT_QUICK_GELU, R, F, C, nullptr, 0}, stream));
+    SETOK_TRY(launch_gemm(GemmArgs{w.u, F, L.w_fc2, F, w.x, C, SETOK_BF16, L.b_fc2, w.x, C, SETOK_BF16, SETOK_ACT_NONE, R, C, F, nullptr, 0}, stream));
+  }
+  // feature_select (clip_encoder.py:40-48)
+  SETOK_TRY(launch_select_rows(w.x, features, feature_dtype, B, T, keep_cls ? 0 : 1, C, stream));
+  return SETOK_OK;
+}
+
+// =================================================================================================
+extern "C" size_t setok_head_workspace_bytes(const setok_head* head, int B, int N) {
+  if (head == nullptr || B <= 0 || N <= 0) return 0;
+  Arena a(nullptr, 0);
+  HeadBufs b;
+  head_carve(head, B, N, a, &b);
+  return a.off;
+}
+
+extern "C" int setok_head_forward(const setok_head* hd, const float* x_pos, const int64_t* idx_cluster, const int32_t* num_clusters,
+                                  const int32_t* offsets, int B, int N, void* tokens, int token_dtype, float* group_features,
+                                  void* workspace, size_t workspace_bytes, setok_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SETOK_REQUIRE(hd && x_pos && idx_cluster && num_clusters && offsets && tokens, SETOK_ERR_BAD_ARG, "head_forward: null pointer");
+  SETOK_REQUIRE(B > 0 && N > 0, SETOK_ERR_BAD_ARG, "head_forward: B=%d N=%d", B, N);
+  const int C = hd->hidden, F = hd->mlp, Ct = hd->token_dim;
+  SETOK_REQUIRE(C > 0 && hd->heads > 0 && C % hd->heads == 0 && C % 8 == 0 && F % 8 == 0 && Ct % 8 == 0, SETOK_ERR_UNSUPPORTED,
+                "head_forward: hidden %d heads %d mlp %d token_dim %d unsupported (multiples of 8 required)", C, hd->heads, F, Ct);
+  SETOK_REQUIRE((C / hd->heads) % 8 == 0 && C / hd->heads <= 512, SETOK_ERR_UNSUPPORTED, "head_forward: head_dim %d unsupported", C / hd->heads);
+  SETOK_TRY(check_block(hd->inner, "inner"));
+  SETOK_TRY(check_block(hd->inter, "inter"));
+  SETOK_REQUIRE(hd->w_out && hd->b_out, SETOK_ERR_BAD_ARG, "head_forward: null out projection");
+  SETOK_REQUIRE(workspace && workspace_bytes >= setok_head_workspace_bytes(hd, B, N), SETOK_ERR_WORKSPACE, "head_forward: workspace too small");
+  const int R = B * N;
+  Arena a(workspace, workspace_bytes);
+  HeadBufs w;
+  head_carve(hd, B, N, a, &w);
+  const int32_t* n_tok = offsets + B;   // device scalar: sum_b K_b
+
+  // group_encoding (tokenizer.py:123-155): tokens sorted by cluster so that every cluster is a contiguous
+  // segment; the Block's linear layers then run over all B*N rows at once and only attention is segmented.
+  SETOK_TRY(launch_sort_by_cluster(idx_cluster, num_clusters, offsets, B, N, w.perm, w.row_seg, w.seg_off, stream));
+  SETOK_TRY(launch_gather_rows(x_pos, w.xs, w.perm, R, C, stream));
+  SETOK_TRY(run_block(hd->inner, C, hd->heads, F, w.xs, R, nullptr, w.seg_off, w.row_seg, w.bb, stream));
+  SETOK_TRY(launch_segment_mean(w.xs, w.seg_off, n_tok, R, C, w.g, group_features, stream));       // tokenizer.py:151
+
+  // inter_encoder over each image's K_b cluster tokens (tokenizer.py:179, repair R2), then `out` (:180)
+  SETOK_TRY(launch_image_segments(offsets, B, w.img_seg, stream));
+  SETOK_TRY(run_block(hd->inter, C, hd->heads, F, w.g, R, n_tok, offsets, w.img_seg, w.bb, stream));
+  SETOK_TRY(launch_convert_rows(w.g, SETOK_F32, w.gb, SETOK_BF16, R, C, SETOK_ACT_NONE, n_tok, stream));
+  SETOK_TRY(launch_gemm(GemmArgs{w.gb, C, hd->w_out, C, tokens, Ct, token_dtype, hd->b_out, nullptr, 0, 0, SETOK_ACT_NONE, R, Ct, C, n_tok, 0}, stream));
+  return SETOK_OK;
+}
+
+// =================================================================================================
+extern "C" size_t setok_project_workspace_bytes(const setok_projector* p, int rows) {
+  if (p == nullptr || rows <= 0 || p->n_linear <= 0) return 0;
+  Arena a(nullptr, 0);
+  int maxd = 0;
+  for (int i = 0; i <= p->n_linear; ++i) maxd = p->dims[i] > maxd ? p->dims[i] : maxd;
+  a.take<bf16>(static_cast<size_t>(rows) * maxd);
+  a.take<bf16>(static_cast<size_t>(rows) * maxd);
+  a.take<float>(static_cast<size_t>(rows) * maxd);
+  return a.off;
+}
+
+extern "C" int setok_project(const setok_projector* p, const void* tokens, int token_dtype, int rows, const int32_t* m_dev,
+                             void* out, int out_dtype, void* workspace, size_t workspace_bytes, setok_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SETOK_REQUIRE(p && tokens && out && rows > 0, SETOK_ERR_BAD_ARG, "project: null pointer or rows <= 0");
+  SETOK_REQUIRE(p->n_linear >= 1 && p->w && p->b && p->dims, SETOK_ERR_BAD_ARG, "project: bad projector description");
+  for (int i = 0; i <= p->n_linear; ++i) SETOK_REQUIRE(p->dims[i] > 0 && p->dims[i] % 8 == 0, SETOK_ERR_UNSUPPORTED, "project: dim %d must be a positive multiple of 8", p->dims[i]);
+  SETOK_REQUIRE(workspace && workspace_bytes >= setok_project_workspace_bytes(p, rows), SETOK_ERR_WORKSPACE, "project: workspace too small");
+  int maxd = 0;
+  for (int i = 0; i <= p->n_linear; ++i) maxd = p->dims[i] > maxd ? p->dims[i] : maxd;
+  Arena a(workspace, workspace_bytes);
+  bf16* ping = a.take<bf16>(static_cast<size_t>(rows) * maxd);
+  bf16* pong = a.take<bf16>(static_cast<size_t>(rows) * maxd);
+  float* tmp = a.take<float>(static_cast<size_t>(rows) * maxd);
+  const void* cur = tokens;
+  if (token_dtype == SETOK_F32) {
+    SETOK_TRY(launch_convert_rows(tokens, SETOK_F32, ping, SETOK_BF16, rows, p->dims[0], SETOK_ACT_NONE, m_dev, stream));
+    cur = ping;
+  } else {
+    SETOK_REQUIRE(token_dtype == SETOK_BF16, SETOK_ERR_BAD_ARG, "project: bad token dtype %d", token_dtype);
+  }
+  const bool use_norm = p->norm_g != nullptr;
+  for (int i = 0; i < p->n_linear; ++i) {
+    const int in_d = p->dims[i], out_d = p->dims[i + 1];
+    const bool last = i == p->n_linear - 1;
+    bf16* dst = (cur == ping) ? pong : ping;
+    SETOK_REQUIRE(p->w[i] && p->b[i], SETOK_ERR_BAD_ARG, "project: null weights for linear %d", i);
+    if (i == 0 && use_norm) {
+      // Linear -> LayerNorm -> (GELU) (builder.py:48-58 with '_Norm')
+      SETOK_TRY(launch_gemm(GemmArgs{cur, in_d, p->w[i], in_d, tmp, out_d, SETOK_F32, p->b[i], nullptr, 0, 0, SETOK_ACT_NONE, rows, out_d, in_d, m_dev, 0}, stream));
+      if (last) {
+        SETOK_TRY(launch_layernorm(tmp, SETOK_F32, out, out_dtype, p->norm_g, p->norm_b, 1e-5f, rows, out_d, nullptr, m_dev, stream));
+      } else {
+        SETOK_TRY(launch_layernorm(tmp, SETOK_F32, tmp, SETOK_F32, p->norm_g, p->norm_b, 1e-5f, rows, out_d, nullptr, m_dev, stream));
+        SETOK_TRY(launch_convert_rows(tmp, SETOK_F32, dst, SETOK_BF16, rows, out_d, SETOK_ACT_GELU_ERF, m_dev, stream));
+        cur = dst;
+      }
+      continue;
+    }
+    if (last) {
+      SETOK_TRY(launch_gemm(GemmArgs{cur, in_d, p->w[i], in_d, out, out_d, out_dtype, p->b[i], nullptr, 0, 0, SETOK_ACT_NONE, rows, out_d, in_d, m_dev, 0}, stream));
+    } else {
+      SETOK_TRY(launch_gemm(GemmArgs{cur, in_d, p->w[i], in_d, dst, out_d, SETOK_BF16, p->b[i], nullptr, 0, 0, SETOK_ACT_GELU_ERF, rows, out_d, in_d, m_dev, 0}, stream));
+      cur = dst;
+    }
+  }
+  return SETOK_OK;
+}

@@ -1,0 +1,278 @@
+// common.cuh — shared host/device helpers for libsetok_b200 (sm_100a only).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/setok_b200.h"
+
+namespace setok {
+
+// ---------------------------------------------------------------------------------------------
+// Host: error reporting (thread-local message), launch accounting
+// ---------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+inline int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  set_error("%s", buf);
+  return code;
+}
+
+#define SETOK_CUDA_OK(expr)                                                                       \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      return ::setok::fail(SETOK_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                           __FILE__, __LINE__);                                                   \
+  } while (0)
+
+// Every kernel launch goes through this: counts the launch and turns launch errors into a status.
+#define SETOK_LAUNCH_CHECK()                                                                      \
+  do {                                                                                            \
+    ::setok::g_launches.fetch_add(1, std::memory_order_relaxed);                                  \
+    cudaError_t _e = cudaGetLastError();                                                          \
+    if (_e != cudaSuccess)                                                                        \
+      return ::setok::fail(SETOK_ERR_CUDA, "kernel launch failed: %s (%s:%d)",                    \
+                           cudaGetErrorString(_e), __FILE__, __LINE__);                           \
+  } while (0)
+
+#define SETOK_REQUIRE(cond, code, ...)                    \
+  do {                                                    \
+    if (!(cond)) return ::setok::fail(code, __VA_ARGS__); \
+  } while (0)
+
+#define SETOK_TRY(expr)          \
+  do {                           \
+    int _s = (expr);             \
+    if (_s != SETOK_OK) return _s; \
+  } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+int num_sms();
+
+// Bump allocator over the caller's workspace (256-byte aligned slices).
+struct Arena {
+  uint8_t* base;
+  size_t cap, off;
+  Arena(void* p, size_t n) : base(static_cast<uint8_t*>(p)), cap(n), off(0) {}
+  template <class T>
+  T* take(size_t count) {
+    size_t bytes = round_up(count * sizeof(T), 256);
+    if (base != nullptr && off + bytes > cap) { off = cap + 1; return nullptr; }
+    T* r = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += bytes;
+    return r;
+  }
+  bool overflow() const { return base != nullptr && off > cap; }
+};
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------------
+// Device helpers
+// ---------------------------------------------------------------------------------------------
+using bf16 = __nv_bfloat16;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(v);
+}
+template <class T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<bf16>(bf16 v) { return __bfloat162float(v); }
+template <class T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float act_quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
+__device__ __forceinline__ float act_gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// ---- mbarrier ------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait: a pipeline bug must surface as a trapped kernel (an error the host sees), never as
+// a hung GPU.  The bound is wall time (4 s), far above any legitimate wait in these kernels.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((++spins & 0x3ffu) == 0) {
+      uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) {
+        printf("setok_b200: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n",
+               blockIdx.x, threadIdx.x, bar, parity);
+        __trap();
+      }
+    }
+  }
+}
+
+// ---- TMA -----------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const void* tmap, uint32_t bar, uint32_t smem_dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const void* tmap, uint32_t bar, uint32_t smem_dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+// ---- tcgen05 / TMEM ---------------------------------------------------------------------------
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_result_addr) {   // whole warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_result_addr), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {            // whole warp (the allocating one)
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]; kind::f16 covers bf16 inputs with fp32 accumulation.
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrives on the mbarrier once all previously issued tcgen05.mma of this thread have completed.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets lane (base_lane + i).
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// K-major, 128-byte-swizzled shared-memory operand descriptor (tile rows of 64 bf16 = 128 B, 8-row
+// swizzle atoms 1024 B apart).  Field layout: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
+// version=1 [46,48) | layout_type=2 (SWIZZLE_128B) [61,64).
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
+  return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor, kind::f16: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, both K-major,
+// N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// ---- legacy warp MMA (used by the small-head_dim attention kernel) --------------------------------
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+#endif  // __CUDACC__
+
+// ---------------------------------------------------------------------------------------------
+// Internal launch API (host), shared between translation units
+// ---------------------------------------------------------------------------------------------
+struct GemmArgs {
+  const void* A; int64_t lda;
+  const void* W; int64_t ldw;
+  void* D; int64_t ldd; int out_dtype;
+  const float* bias;
+  const void* residual; int64_t ldr; int residual_dtype;
+  int act;
+  int M, N, K;
+  const int32_t* m_dev;
+  int remap_P;   // >0: patch-embed mode: out row r -> r + r/P + 1, residual row -> 1 + r%P (pos-emb broadcast)
+};
+int launch_gemm(const GemmArgs& g, cudaStream_t stream);
+
+int launch_layernorm(const void* in, int in_dtype, void* out, int out_dtype, const float* gamma, const float* beta,
+                     float eps, int rows, int C, const int32_t* gather, const int32_t* m_dev, cudaStream_t stream);
+int launch_attention(const void* qkv, void* out, int rows, int C, int heads, float scale, const int32_t* seg_off,
+                     const int32_t* row_seg, int uniform_T, const int32_t* m_dev, cudaStream_t stream);
+
+}  // namespace setok

@@ -1,0 +1,279 @@
+// gemm_tcgen05.cu — persistent, warp-specialised bf16 GEMM for sm_100a.
+//
+//   D[M,N] = epilogue(A[M,K] * W[N,K]^T),  fp32 accumulation in TMEM.
+//
+// One CTA per SM, 192 threads:
+//   warp 0      TMA producer   (cp.async.bulk.tensor 2-D, 128B swizzle, 4-stage mbarrier ring)
+//   warp 1      MMA issuer     (one thread: tcgen05.mma.cta_group::1.kind::f16, 128x256x16 per instr),
+//               owns the TMEM allocation (512 columns = two 128x256 fp32 accumulators)
+//   warps 2..5  epilogue       (tcgen05.ld -> per-warp smem transpose -> coalesced bias/act/residual/store)
+// The two accumulators let the epilogue of tile i overlap the MMAs of tile i+1.  Tiles are walked
+// N-fastest so the CTAs running concurrently share A row-blocks through L2 while W (<= 8 MB) stays
+// L2-resident.  M may be ragged (TMA zero-fills / the epilogue masks) and may live on the device
+// (m_dev) so data-dependent row counts need no host sync.
+#include "common.cuh"
+
+namespace setok {
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UMMA_K = 16;
+constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KiB
+constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KiB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int EPI_WARPS = 4;
+constexpr int STG_BYTES_PER_WARP = 32 * 64 * 4;   // 32 rows x 64 fp32 columns
+constexpr int OFF_A = 0;
+constexpr int OFF_B = STAGES * A_STAGE_BYTES;
+constexpr int OFF_STG = OFF_B + STAGES * B_STAGE_BYTES;
+constexpr int OFF_BAR = OFF_STG + EPI_WARPS * STG_BYTES_PER_WARP;
+constexpr int NUM_BARS = 2 * STAGES + 4;
+constexpr int SMEM_BYTES = OFF_BAR + NUM_BARS * 8 + 16 + 1024;   // + tmem ptr + alignment slack
+constexpr int THREADS = 192;
+constexpr int TMEM_COLS = 512;
+
+struct GemmDev {
+  void* D; long long ldd;
+  const float* bias;
+  const void* res; long long ldr;
+  const int32_t* m_dev;
+  int M, N, K;
+  int act, out_f32, res_kind, remap_P;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const uint32_t bar0 = base + OFF_BAR;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 + a); };
+  volatile uint32_t* tmem_holder = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + NUM_BARS * 8);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(base + OFF_BAR + NUM_BARS * 8);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  int M_eff = p.M;
+  if (p.m_dev != nullptr) { int m = *p.m_dev; M_eff = m < p.M ? (m < 0 ? 0 : m) : p.M; }
+  const int tiles_m = (M_eff + BM - 1) / BM;
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int k_blocks = (p.K + BK - 1) / BK;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m_blk = t / tiles_n, n_blk = t % tiles_n;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+          tma_load_2d(&tmA, full_bar(stage), base + OFF_A + stage * A_STAGE_BYTES, kb * BK, m_blk * BM);
+          tma_load_2d(&tmB, full_bar(stage), base + OFF_B + stage * B_STAGE_BYTES, kb * BK, n_blk * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint32_t a_addr = base + OFF_A + stage * A_STAGE_BYTES;
+          const uint32_t b_addr = base + OFF_B + stage * B_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t adesc = umma_desc_k_sw128(a_addr + k * UMMA_K * 2);
+            const uint64_t bdesc = umma_desc_k_sw128(b_addr + k * UMMA_K * 2);
+            umma_f16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));          // smem slot reusable once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));              // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    uint8_t* stg = smem + OFF_STG + (warp - 2) * STG_BYTES_PER_WARP;
+    int acc = 0; uint32_t acc_phase = 0;
+    const int j = lane & 15;                      // 16-byte column chunk handled in the coalesced phase
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int m_blk = t / tiles_n, n_blk = t % tiles_n;
+      const int row0 = m_blk * BM + q * 32;
+      const int n0 = n_blk * BN;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 64; ++ch) {
+        const int gcol0 = n0 + ch * 64;
+        if (gcol0 >= p.N) break;
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32b_x32(taddr + ch * 64, r0);
+        tmem_ld_32x32b_x32(taddr + ch * 64 + 32, r1);
+        tmem_ld_wait();
+        // transpose through smem: thread `lane` owns tile row q*32+lane, 64 fp32 columns
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          *reinterpret_cast<uint4*>(stg + lane * 256 + ((c ^ (lane & 7)) << 4)) =
+              make_uint4(r0[4 * c], r0[4 * c + 1], r0[4 * c + 2], r0[4 * c + 3]);
+          *reinterpret_cast<uint4*>(stg + lane * 256 + (((c + 8) ^ (lane & 7)) << 4)) =
+              make_uint4(r1[4 * c], r1[4 * c + 1], r1[4 * c + 2], r1[4 * c + 3]);
+        }
+        __syncwarp();
+        const int col = gcol0 + 4 * j;
+        const bool col_ok = col < p.N;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col_ok && p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+#pragma unroll 4
+        for (int it = 0; it < 16; ++it) {
+          const int r = it * 2 + (lane >> 4);
+          const int grow = row0 + r;
+          float4 v = *reinterpret_cast<const float4*>(stg + r * 256 + ((j ^ (r & 7)) << 4));
+          if (grow < M_eff && col_ok) {
+            v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+            if (p.act == SETOK_ACT_QUICK_GELU) {
+              v.x = act_quick_gelu(v.x); v.y = act_quick_gelu(v.y); v.z = act_quick_gelu(v.z); v.w = act_quick_gelu(v.w);
+            } else if (p.act == SETOK_ACT_GELU_ERF) {
+              v.x = act_gelu_erf(v.x); v.y = act_gelu_erf(v.y); v.z = act_gelu_erf(v.z); v.w = act_gelu_erf(v.w);
+            }
+            long long orow = grow, rrow = grow;
+            if (p.remap_P > 0) { orow = grow + grow / p.remap_P + 1; rrow = 1 + grow % p.remap_P; }
+            if (p.res_kind == 1) {
+              const uint2 u = *reinterpret_cast<const uint2*>(static_cast<const bf16*>(p.res) + rrow * p.ldr + col);
+              const float2 lo = unpack_bf16x2(u.x), hi = unpack_bf16x2(u.y);
+              v.x += lo.x; v.y += lo.y; v.z += hi.x; v.w += hi.y;
+            } else if (p.res_kind == 2) {
+              const float4 rr = *reinterpret_cast<const float4*>(static_cast<const float*>(p.res) + rrow * p.ldr + col);
+              v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+            }
+            if (p.out_f32) {
+              *reinterpret_cast<float4*>(static_cast<float*>(p.D) + orow * p.ldd + col) = v;
+            } else {
+              *reinterpret_cast<uint2*>(static_cast<bf16*>(p.D) + orow * p.ldd + col) =
+                  make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+            }
+          }
+        }
+        __syncwarp();
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---- host --------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+int make_tmap_2d_bf16(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(SETOK_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (driver too old?)");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(SETOK_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu ld=%llu)", (int)r,
+                (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems);
+  return SETOK_OK;
+}
+
+}  // namespace
+
+int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
+  SETOK_REQUIRE(g.A && g.W && g.D, SETOK_ERR_BAD_ARG, "gemm: null operand");
+  SETOK_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, SETOK_ERR_BAD_ARG, "gemm: non-positive shape M=%d N=%d K=%d", g.M, g.N, g.K);
+  SETOK_REQUIRE(g.K % 8 == 0 && g.N % 8 == 0, SETOK_ERR_UNSUPPORTED, "gemm: K (%d) and N (%d) must be multiples of 8", g.K, g.N);
+  SETOK_REQUIRE(g.lda % 8 == 0 && g.ldw % 8 == 0 && g.lda >= g.K && g.ldw >= g.K, SETOK_ERR_BAD_ARG,
+                "gemm: lda/ldw must be multiples of 8 and >= K (lda=%lld ldw=%lld K=%d)", (long long)g.lda, (long long)g.ldw, g.K);
+  SETOK_REQUIRE(aligned16(g.A) && aligned16(g.W) && aligned16(g.D), SETOK_ERR_BAD_ARG, "gemm: operands must be 16-byte aligned");
+  SETOK_REQUIRE(g.ldd % 4 == 0 && g.ldd >= g.N, SETOK_ERR_BAD_ARG, "gemm: ldd (%lld) must be a multiple of 4 and >= N", (long long)g.ldd);
+  SETOK_REQUIRE(g.out_dtype == SETOK_F32 || g.out_dtype == SETOK_BF16, SETOK_ERR_BAD_ARG, "gemm: bad out_dtype %d", g.out_dtype);
+  SETOK_REQUIRE(g.act >= 0 && g.act <= 2, SETOK_ERR_BAD_ARG, "gemm: bad activation %d", g.act);
+  if (g.residual) {
+    SETOK_REQUIRE(aligned16(g.residual) && g.ldr % 4 == 0, SETOK_ERR_BAD_ARG, "gemm: residual must be 16-byte aligned, ldr %% 4 == 0");
+    SETOK_REQUIRE(g.residual_dtype == SETOK_F32 || g.residual_dtype == SETOK_BF16, SETOK_ERR_BAD_ARG, "gemm: bad residual dtype");
+  }
+  if (g.bias) SETOK_REQUIRE(aligned16(g.bias), SETOK_ERR_BAD_ARG, "gemm: bias must be 16-byte aligned");
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    SETOK_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  CUtensorMap tmA, tmB;
+  SETOK_TRY(make_tmap_2d_bf16(&tmA, g.A, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)g.lda, BM));
+  SETOK_TRY(make_tmap_2d_bf16(&tmB, g.W, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldw, BN));
+  GemmDev p;
+  p.D = g.D; p.ldd = g.ldd; p.bias = g.bias; p.res = g.residual; p.ldr = g.ldr; p.m_dev = g.m_dev;
+  p.M = g.M; p.N = g.N; p.K = g.K; p.act = g.act; p.out_f32 = g.out_dtype == SETOK_F32;
+  p.res_kind = g.residual ? (g.residual_dtype == SETOK_BF16 ? 1 : 2) : 0;
+  p.remap_P = g.remap_P;
+  const int tiles = ceil_div(g.M, BM) * ceil_div(g.N, BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_bf16_tcgen05_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
+  SETOK_LAUNCH_CHECK();
+  return SETOK_OK;
+}
+
+}  // namespace setok
+
+extern "C" int setok_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* D, int64_t ldd, int out_dtype,
+                               const float* bias, const void* residual, int64_t ldr, int residual_dtype, int act, int M,
+                               int N, int K, const int32_t* m_dev, setok_stream_t stream) {
+  setok::GemmArgs g{A, lda, W, ldw, D, ldd, out_dtype, bias, residual, ldr, residual_dtype, act, M, N, K, m_dev, 0};
+  return setok::launch_gemm(g, static_cast<cudaStream_t>(stream));
+}

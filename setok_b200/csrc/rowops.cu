@@ -1,0 +1,375 @@
+// rowops.cu — bandwidth-bound row kernels around the GEMMs: LayerNorm, im2col for the patch embedding,
+// CLS rows, feature selection, cluster sort / gather, segment mean.  All are coalesced, vectorised
+// (16-byte accesses where the layout allows) and sized in whole waves of the 148 SMs by grid-stride.
+#include "common.cuh"
+#include "rowops.cuh"
+
+namespace setok {
+namespace {
+
+template <class T> struct Vec4;
+template <> struct Vec4<float> {
+  static __device__ __forceinline__ float4 load(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  static __device__ __forceinline__ void store(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+};
+template <> struct Vec4<bf16> {
+  static __device__ __forceinline__ float4 load(const bf16* p) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  static __device__ __forceinline__ void store(bf16* p, float4 v) {
+    *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+};
+
+__device__ __forceinline__ int live_rows(int rows, const int32_t* m_dev) {
+  if (m_dev == nullptr) return rows;
+  const int m = *m_dev;
+  return m < rows ? (m < 0 ? 0 : m) : rows;
+}
+
+// ---- LayerNorm: one warp per row, row cached in registers when C <= 1024 -----------------------
+constexpr int LN_MAXV = 8;   // float4 vectors per lane held in registers (C <= 1024)
+
+template <class TI, class TO>
+__global__ void __launch_bounds__(256) layernorm_kernel(const TI* __restrict__ in, TO* __restrict__ out,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        float eps, int rows, int C, const int32_t* __restrict__ gather,
+                                                        const int32_t* __restrict__ m_dev) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int n = live_rows(rows, m_dev);
+  const int nvec = C >> 2;
+  const bool cached = nvec <= LN_MAXV * 32;
+  const float invC = 1.0f / static_cast<float>(C);
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < n; r += gridDim.x * wpb) {
+    const long long src = gather ? gather[r] : r;
+    const TI* x = in + src * C;
+    float4 v[LN_MAXV];
+    float s = 0.f;
+    if (cached) {
+#pragma unroll
+      for (int i = 0; i < LN_MAXV; ++i) {
+        const int vi = lane + i * 32;
+        if (vi < nvec) { v[i] = Vec4<TI>::load(x + vi * 4); s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
+      }
+    } else {
+      for (int vi = lane; vi < nvec; vi += 32) { const float4 t = Vec4<TI>::load(x + vi * 4); s += (t.x + t.y) + (t.z + t.w); }
+    }
+    const float mean = warp_sum(s) * invC;
+    float q = 0.f;
+    if (cached) {
+#pragma unroll
+      for (int i = 0; i < LN_MAXV; ++i) {
+        const int vi = lane + i * 32;
+        if (vi < nvec) {
+          const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+          q += (a * a + b * b) + (c * c + d * d);
+        }
+      }
+    } else {
+      for (int vi = lane; vi < nvec; vi += 32) {
+        const float4 t = Vec4<TI>::load(x + vi * 4);
+        const float a = t.x - mean, b = t.y - mean, c = t.z - mean, d = t.w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) * invC + eps);
+    TO* y = out + static_cast<long long>(r) * C;
+    if (cached) {
+#pragma unroll
+      for (int i = 0; i < LN_MAXV; ++i) {
+        const int vi = lane + i * 32;
+        if (vi < nvec) {
+          const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + vi);
+          const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + vi);
+          float4 o;
+          o.x = (v[i].x - mean) * rstd * g.x + b.x; o.y = (v[i].y - mean) * rstd * g.y + b.y;
+          o.z = (v[i].z - mean) * rstd * g.z + b.z; o.w = (v[i].w - mean) * rstd * g.w + b.w;
+          Vec4<TO>::store(y + vi * 4, o);
+        }
+      }
+    } else {
+      for (int vi = lane; vi < nvec; vi += 32) {
+        const float4 t = Vec4<TI>::load(x + vi * 4);
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + vi);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + vi);
+        float4 o;
+        o.x = (t.x - mean) * rstd * g.x + b.x; o.y = (t.y - mean) * rstd * g.y + b.y;
+        o.z = (t.z - mean) * rstd * g.z + b.z; o.w = (t.w - mean) * rstd * g.w + b.w;
+        Vec4<TO>::store(y + vi * 4, o);
+      }
+    }
+  }
+}
+
+// ---- patch embedding im2col: images [B,3,H,W] -> A [B*P, Kp] bf16, columns (c, ky, kx), zero pad ----
+template <class TI>
+__global__ void __launch_bounds__(256) im2col_kernel(const TI* __restrict__ img, bf16* __restrict__ A, int B, int H, int W,
+                                                     int patch, int Kp) {
+  const int gw = W / patch, gh = H / patch;
+  const int K = 3 * patch * patch;
+  const long long total = static_cast<long long>(B) * gh * gw * (Kp / 2);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cp = static_cast<int>(i % (Kp / 2));
+    const long long row = i / (Kp / 2);
+    const int px = static_cast<int>(row % gw);
+    const int py = static_cast<int>((row / gw) % gh);
+    const int b = static_cast<int>(row / (static_cast<long long>(gw) * gh));
+    float v[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int col = cp * 2 + e;
+      if (col < K) {
+        const int c = col / (patch * patch);
+        const int rem = col % (patch * patch);
+        const int ky = rem / patch, kx = rem % patch;
+        v[e] = to_f32<TI>(img[((static_cast<long long>(b) * 3 + c) * H + (py * patch + ky)) * W + (px * patch + kx)]);
+      } else {
+        v[e] = 0.f;
+      }
+    }
+    *reinterpret_cast<uint32_t*>(A + row * Kp + cp * 2) = pack_bf16x2(v[0], v[1]);
+  }
+}
+
+// emb[b*T + 0, :] = cls + pos[0]   (fp32)
+__global__ void cls_rows_kernel(float* __restrict__ emb, const float* __restrict__ cls, const float* __restrict__ pos,
+                                int B, int T, int C) {
+  const int total = B * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i / C, c = i % C;
+    emb[static_cast<long long>(b) * T * C + c] = cls[c] + pos[c];
+  }
+}
+
+// features[b, t', :] = x[b*T + skip + t', :]  (dtype conversion bf16 -> out)
+template <class TO>
+__global__ void __launch_bounds__(256) select_rows_kernel(const bf16* __restrict__ x, TO* __restrict__ out, int B, int T, int skip, int C) {
+  const int To = T - skip;
+  const int nvec = C >> 2;
+  const long long total = static_cast<long long>(B) * To * nvec;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int vi = static_cast<int>(i % nvec);
+    const long long r = i / nvec;
+    const int t = static_cast<int>(r % To);
+    const long long b = r / To;
+    const float4 v = Vec4<bf16>::load(x + ((b * T + skip + t) * C + vi * 4));
+    Vec4<TO>::store(out + (r * C + vi * 4), v);
+  }
+}
+
+// ---- cluster bookkeeping -------------------------------------------------------------------------
+// One CTA per image: stable counting sort of the image's N tokens by cluster label.
+//   perm[b*N + p]    = global source row (b*N + t) of the token at sorted position p
+//   row_seg[b*N + p] = global cluster id (offsets[b] + label)
+//   seg_off[g]       = first sorted row of global cluster g; seg_off[offsets[B]] = B*N
+__global__ void __launch_bounds__(256) sort_by_cluster_kernel(const int64_t* __restrict__ idx_cluster,
+                                                              const int32_t* __restrict__ num_clusters,
+                                                              const int32_t* __restrict__ offsets, int B, int N,
+                                                              int32_t* __restrict__ perm, int32_t* __restrict__ row_seg,
+                                                              int32_t* __restrict__ seg_off) {
+  extern __shared__ int32_t sm[];
+  int32_t* lab = sm;            // [N]
+  int32_t* cnt = sm + N;        // [N]  counts, then exclusive starts
+  const int b = blockIdx.x;
+  const int K = num_clusters[b];
+  const int goff = offsets[b];
+  for (int t = threadIdx.x; t < N; t += blockDim.x) { lab[t] = static_cast<int32_t>(idx_cluster[static_cast<long long>(b) * N + t]); cnt[t] = 0; }
+  __syncthreads();
+  for (int t = threadIdx.x; t < N; t += blockDim.x) atomicAdd(&cnt[lab[t]], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int c = 0; c < K; ++c) { const int n = cnt[c]; cnt[c] = run; run += n; }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < K; c += blockDim.x) {
+    int pos = cnt[c];
+    seg_off[goff + c] = b * N + pos;
+    for (int t = 0; t < N; ++t) {
+      if (lab[t] == c) { perm[b * N + pos] = b * N + t; row_seg[b * N + pos] = goff + c; ++pos; }
+    }
+  }
+  if (b == B - 1 && threadIdx.x == 0) seg_off[goff + K] = B * N;
+}
+
+// out[r, :] = in[perm[r], :]   (fp32 rows)
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                          const int32_t* __restrict__ perm, int rows, int C) {
+  const int nvec = C >> 2;
+  const long long total = static_cast<long long>(rows) * nvec;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int vi = static_cast<int>(i % nvec);
+    const long long r = i / nvec;
+    reinterpret_cast<float4*>(out)[r * nvec + vi] = reinterpret_cast<const float4*>(in)[static_cast<long long>(perm[r]) * nvec + vi];
+  }
+}
+
+// out[g, :] = mean over rows [seg_off[g], seg_off[g+1]) of x   (fp32), g < *n_seg_dev
+__global__ void __launch_bounds__(256) segment_mean_kernel(const float* __restrict__ x, const int32_t* __restrict__ seg_off,
+                                                           const int32_t* __restrict__ n_seg_dev, int cap, int C,
+                                                           float* __restrict__ out, float* __restrict__ out2) {
+  const int nvec = C >> 2;
+  const int nseg = live_rows(cap, n_seg_dev);
+  for (int g = blockIdx.x; g < nseg; g += gridDim.x) {
+    const int r0 = seg_off[g], r1 = seg_off[g + 1];
+    const float inv = 1.0f / static_cast<float>(r1 - r0);
+    for (int vi = threadIdx.x; vi < nvec; vi += blockDim.x) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = r0; r < r1; ++r) {
+        const float4 t = reinterpret_cast<const float4*>(x)[static_cast<long long>(r) * nvec + vi];
+        s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+      }
+      s.x *= inv; s.y *= inv; s.z *= inv; s.w *= inv;
+      reinterpret_cast<float4*>(out)[static_cast<long long>(g) * nvec + vi] = s;
+      if (out2) reinterpret_cast<float4*>(out2)[static_cast<long long>(g) * nvec + vi] = s;
+    }
+  }
+}
+
+// row_seg[r] = image index for the packed token rows; used by the inter-cluster encoder
+__global__ void __launch_bounds__(256) image_segments_kernel(const int32_t* __restrict__ offsets, int B, int32_t* __restrict__ row_seg) {
+  const int b = blockIdx.x;
+  for (int r = offsets[b] + threadIdx.x; r < offsets[b + 1]; r += blockDim.x) row_seg[r] = b;
+}
+
+template <class TI, class TO>
+__global__ void __launch_bounds__(256) convert_kernel(const TI* __restrict__ in, TO* __restrict__ out, long long n4) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    Vec4<TO>::store(out + i * 4, Vec4<TI>::load(in + i * 4));
+}
+
+// out[r, :] = (TO) act(in[r, :]) for r < live rows; act: 0 none, 2 GELU(erf)
+template <class TI, class TO>
+__global__ void __launch_bounds__(256) convert_rows_kernel(const TI* __restrict__ in, TO* __restrict__ out, int rows, int C, int act,
+                                                           const int32_t* __restrict__ m_dev) {
+  const int nvec = C >> 2;
+  const long long total = static_cast<long long>(live_rows(rows, m_dev)) * nvec;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 v = Vec4<TI>::load(in + i * 4);
+    if (act == SETOK_ACT_GELU_ERF) { v.x = act_gelu_erf(v.x); v.y = act_gelu_erf(v.y); v.z = act_gelu_erf(v.z); v.w = act_gelu_erf(v.w); }
+    Vec4<TO>::store(out + i * 4, v);
+  }
+}
+
+inline int grid_for(long long work_items, int threads, int max_waves = 8) {
+  long long blocks = (work_items + threads - 1) / threads;
+  const long long cap = static_cast<long long>(num_sms()) * max_waves;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+}  // namespace
+
+int launch_layernorm(const void* in, int in_dtype, void* out, int out_dtype, const float* gamma, const float* beta, float eps,
+                     int rows, int C, const int32_t* gather, const int32_t* m_dev, cudaStream_t stream) {
+  SETOK_REQUIRE(in && out && gamma && beta, SETOK_ERR_BAD_ARG, "layernorm: null pointer");
+  SETOK_REQUIRE(rows > 0 && C > 0 && C % 4 == 0, SETOK_ERR_UNSUPPORTED, "layernorm: rows=%d C=%d (C must be a multiple of 4)", rows, C);
+  SETOK_REQUIRE(aligned16(in) && aligned16(out) && aligned16(gamma) && aligned16(beta), SETOK_ERR_BAD_ARG, "layernorm: buffers must be 16-byte aligned");
+  const int wpb = 8;
+  int grid = ceil_div(rows, wpb);
+  const int cap = num_sms() * 8;
+  if (grid > cap) grid = cap;
+#define LN_CASE(TI, TO) layernorm_kernel<TI, TO><<<grid, wpb * 32, 0, stream>>>(static_cast<const TI*>(in), static_cast<TO*>(out), gamma, beta, eps, rows, C, gather, m_dev)
+  if (in_dtype == SETOK_F32 && out_dtype == SETOK_F32) LN_CASE(float, float);
+  else if (in_dtype == SETOK_F32 && out_dtype == SETOK_BF16) LN_CASE(float, bf16);
+  else if (in_dtype == SETOK_BF16 && out_dtype == SETOK_BF16) LN_CASE(bf16, bf16);
+  else if (in_dtype == SETOK_BF16 && out_dtype == SETOK_F32) LN_CASE(bf16, float);
+  else return fail(SETOK_ERR_BAD_ARG, "layernorm: bad dtypes %d -> %d", in_dtype, out_dtype);
+#undef LN_CASE
+  SETOK_LAUNCH_CHECK();
+  return SETOK_OK;
+}
+
+int launch_im2col(const void* images, int image_dtype, void* A, int B, int H, int W, int patch, int Kp, cudaStream_t stream) {
+  const long long total = static_cast<long long>(B) * (H / patch) * (W / patch) * (Kp / 2);
+  const int grid = grid_for(total, 256, 16);
+  if (image_dtype == SETOK_F32) im2col_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(images), static_cast<bf16*>(A), B, H, W, patch, Kp);
+  else if (image_dtype == SETOK_BF16) im2col_kernel<bf16><<<grid, 256, 0, stream>>>(static_cast<const bf16*>(images), static_cast<bf16*>(A), B, H, W, patch, Kp);
+  else return fail(SETOK_ERR_BAD_ARG, "im2col: bad image dtype %d", image_dtype);
+  SETOK_LAUNCH_CHECK();
+  return SETOK_OK;
+}
+
+int launch_cls_rows(float* emb, const float* cls, const float* pos, int B, int T, int C, cudaStream_t stream) {
+  cls_rows_kernel<<<grid_for(static_cast<long long>(B) * C, 256), 256, 0, stream>>>(emb, cls, pos, B, T, C);
+  SETOK_LAUNCH_CHECK();
+  return SETOK_OK;
+}
+
+int launch_select_rows(const void* x_bf16, void* out, int out_dtype, int B, int T, int skip, int C, cudaStream_t stream) {
+  const long long total = static_cast<long long>(B) * (T - skip) * (C / 4);
+  const int grid = grid_for(total, 256, 16);
+  if (out_dtype == SETOK_F32) select_rows_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const bf16*>(x_bf16), static_cast<float*>(out), B, T, skip, C);
+  else if (out_dtype == SETOK_BF16) select_rows_kernel<bf16><<<grid, 256, 0, stream>>>(static_cast<const bf16*>(x_bf16), static_cast<bf16*>(out), B, T, skip, C);
+  else return fail(SETOK_ERR_BAD_ARG, "select_rows: bad dtype %d", out_dtype);
+  SETOK_LAUNCH_CHECK();
+  return SETOK_OK;
+}
+
+int launch_sort_by_cluster(const int64_t* idx_cluster, const int32_t* num_clusters, const int32_t* offsets, int B, int N,
+                           int32_t* perm, int32_t* row_seg, int32_t* seg_off, cudaStream_t stream) {
+  sort_by_cluster_kernel<<<B, 256, 2 * N * sizeof(int32_t), stream>>>(idx_cluster, num_clusters, offsets, B, N, perm, row_seg, seg_off);
+  SETOK_LAUNCH_CHECK();
+  return SETOK_OK;
+}
+
+int launch_gather_rows(const float* in, float* out, const int32_t* perm, int rows, int C, cudaStream_t stream) {
+  gather_rows_kernel<<<grid_for(static_cast<long long>(rows) * (C / 4), 256, 16), 256, 0, stream>>>(in, out, perm, rows, C);
+  SETOK_LAUNCH_CHECK();
+  return SETOK_OK;
+}
+
+int launch_segment_mean(const float* x, const int32_t* seg_off, const int32_t* n_seg_dev, int cap, int C, float* out,
+                        float* out2, cudaStream_t stream) {
+  int grid = cap < num_sms() * 8 ? cap : num_sms() * 8;
+  segment_mean_kernel<<<grid, 256, 0, stream>>>(x, seg_off, n_seg_dev, cap, C, out, out2);
+  SETOK_LAUNCH_CHECK();
+  return SETOK_OK;
+}
+
+int launch_image_segments(const int32_t* offsets, int B, int32_t* row_seg, cudaStream_t stream) {
+  image_segments_kernel<<<B, 256, 0, stream>>>(offsets, B, row_seg);
+  SETOK_LAUNCH_CHECK();
+  return SETOK_OK;
+}
+
+int launch_convert(const void* in, int in_dtype, void* out, int out_dtype, long long n, cudaStream_t stream) {
+  SETOK_REQUIRE(n % 4 == 0, SETOK_ERR_UNSUPPORTED, "convert: element count must be a multiple of 4");
+  const int grid = grid_for(n / 4, 256, 16);
+  if (in_dtype == SETOK_F32 && out_dtype == SETOK_BF16) convert_kernel<float, bf16><<<grid, 256, 0, stream>>>(static_cast<const float*>(in), static_cast<bf16*>(out), n / 4);
+  else if (in_dtype == SETOK_BF16 && out_dtype == SETOK_F32) convert_kernel<bf16, float><<<grid, 256, 0, stream>>>(static_cast<const bf16*>(in), static_cast<float*>(out), n / 4);
+  else return fail(SETOK_ERR_BAD_ARG, "convert: unsupported dtype pair %d -> %d", in_dtype, out_dtype);
+  SETOK_LAUNCH_CHECK();
+  return SETOK_OK;
+}
+
+int launch_convert_rows(const void* in, int in_dtype, void* out, int out_dtype, int rows, int C, int act, const int32_t* m_dev,
+                        cudaStream_t stream) {
+  SETOK_REQUIRE(C % 4 == 0, SETOK_ERR_UNSUPPORTED, "convert_rows: C must be a multiple of 4");
+  const int grid = grid_for(static_cast<long long>(rows) * (C / 4), 256, 16);
+#define CV_CASE(TI, TO) convert_rows_kernel<TI, TO><<<grid, 256, 0, stream>>>(static_cast<const TI*>(in), static_cast<TO*>(out), rows, C, act, m_dev)
+  if (in_dtype == SETOK_F32 && out_dtype == SETOK_BF16) CV_CASE(float, bf16);
+  else if (in_dtype == SETOK_BF16 && out_dtype == SETOK_F32) CV_CASE(bf16, float);
+  else if (in_dtype == SETOK_BF16 && out_dtype == SETOK_BF16) CV_CASE(bf16, bf16);
+  else if (in_dtype == SETOK_F32 && out_dtype == SETOK_F32) CV_CASE(float, float);
+  else return fail(SETOK_ERR_BAD_ARG, "convert_rows: bad dtypes %d -> %d", in_dtype, out_dtype);
+#undef CV_CASE
+  SETOK_LAUNCH_CHECK();
+  return SETOK_OK;
+}
+
+}  // namespace setok
+
+extern "C" int setok_layernorm(const void* in, int in_dtype, void* out, int out_dtype, const float* gamma, const float* beta,
+                               float eps, int rows, int C, const int32_t* gather, const int32_t* m_dev, setok_stream_t stream) {
+  return setok::launch_layernorm(in, in_dtype, out, out_dtype, gamma, beta, eps, rows, C, gather, m_dev, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,19 @@
+// rowops.cuh — host launch declarations for the row kernels (rowops.cu) and clustering kernels (dpc.cu).
+#pragma once
+#include "common.cuh"
+
+namespace setok {
+int launch_im2col(const void* images, int image_dtype, void* A, int B, int H, int W, int patch, int Kp, cudaStream_t stream);
+int launch_cls_rows(float* emb, const float* cls, const float* pos, int B, int T, int C, cudaStream_t stream);
+int launch_select_rows(const void* x_bf16, void* out, int out_dtype, int B, int T, int skip, int C, cudaStream_t stream);
+int launch_sort_by_cluster(const int64_t* idx_cluster, const int32_t* num_clusters, const int32_t* offsets, int B, int N,
+                           int32_t* perm, int32_t* row_seg, int32_t* seg_off, cudaStream_t stream);
+int launch_gather_rows(const float* in, float* out, const int32_t* perm, int rows, int C, cudaStream_t stream);
+int launch_segment_mean(const float* x, const int32_t* seg_off, const int32_t* n_seg_dev, int cap, int C, float* out,
+                        float* out2, cudaStream_t stream);
+int launch_image_segments(const int32_t* offsets, int B, int32_t* row_seg, cudaStream_t stream);
+int launch_convert(const void* in, int in_dtype, void* out, int out_dtype, long long n, cudaStream_t stream);
+int launch_convert_rows(const void* in, int in_dtype, void* out, int out_dtype, int rows, int C, int act, const int32_t* m_dev,
+                        cudaStream_t stream);
+int get_pos_table(int h, int w, int C, const float** out, cudaStream_t stream);
+}  // namespace setok

@@ -1,0 +1,148 @@
+"""GPU parity of the fused pos-add + DPC-kNN clustering against the golden vectors produced by the
+reference's own source and against the CPU oracle.  Integer outputs (index_down, idx_cluster) must be
+bit-exact; score within 1e-5 relative."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():
+    pytest.skip("CUDA device required", allow_module_level=True)
+
+from conftest import load_golden  # noqa: E402
+from oracle import setok_oracle as O  # noqa: E402
+from setok_b200 import ops  # noqa: E402
+
+DEV = torch.device("cuda:0")
+T = lambda a: torch.from_numpy(np.asarray(a))
+
+
+def _run(x, noise, k, thr, mcn, token_mask=None):
+    """x: (B, N, C) *already position-embedded* features -> feed with a zero pos table."""
+    B, N, C = x.shape
+    h = N
+    zero_pos = torch.zeros(N, C, device=DEV)
+    return ops.dpc_cluster(x.to(DEV).contiguous(), noise.to(DEV).contiguous(), (N, 1), k, thr, mcn, pos_table=zero_pos,
+                           token_mask=None if token_mask is None else token_mask.to(DEV))
+
+
+def test_dpc_golden_bit_exact():
+    g = load_golden("dpc_knn")
+    for name in g["names"]:
+        name = str(name)
+        k, thr, mcn = g[name + "/params"]
+        x = T(g[name + "/x"])[None]
+        noise = T(g[name + "/noise"])[None]
+        tm = T(g[name + "/token_mask"])[None] if (name + "/token_mask") in g.files else None
+        x_pos, idx, score, down, numc, offs = _run(x, noise, int(k), float(thr), int(mcn), tm)
+        K = int(numc[0])
+        ref_down = T(g[name + "/index_down"])
+        assert K == ref_down.numel(), f"{name}: K {K} != {ref_down.numel()}"
+        assert torch.equal(down[0, :K].cpu(), ref_down), name
+        assert (down[0, K:] == -1).all()
+        assert torch.equal(idx[0].cpu(), T(g[name + "/idx_cluster"])), name
+        # score = parent distance x density; the distance comes out of the cancelling n_i + n_j - 2 x_i.x_j form that
+        # torch.cdist uses, so a different (equally valid) fp32 summation order moves it by ~1e-4 relative
+        torch.testing.assert_close(score[0].cpu(), T(g[name + "/score"]).reshape(-1), rtol=1e-3, atol=1e-5)
+        assert offs.tolist() == [0, K]
+        assert torch.equal(x_pos[0].cpu(), x[0])
+
+
+def _well_posed_image(N, C, G, k, mcn, pos, seed0):
+    """A seeded image whose centre-selection decision has a margin well above fp32 reassociation error."""
+    for t in range(40):
+        seed = seed0 + t
+        f = O.mog_features(N, C, G, 0.05, seed) if G else torch.randn(N, C, generator=torch.Generator().manual_seed(seed))
+        noise = O.tie_noise(N, seed + 5000)
+        m = O.dpc_margins(f + pos, k, noise, 0.5, mcn)
+        if m["threshold_margin"] > 2e-4:
+            return f, noise, m
+    raise AssertionError("no well-posed seed found")
+
+
+@pytest.mark.parametrize("N,C,G,k", [(256, 1024, 32, 16), (576, 1024, 64, 16), (1024, 1024, 128, 16), (196, 768, 0, 32), (256, 1024, 0, 64)])
+def test_dpc_vs_oracle_batched(N, C, G, k):
+    """A batch of independent images at the BASELINE shapes; pos-embedding add included (h = w = sqrt N).
+    Centres must be bit-exact; labels must be bit-exact for every token whose two nearest centres are more than
+    2e-4 apart in the oracle (closer than that, the reference's own cdist rounding decides)."""
+    B = 6
+    h = int(math.sqrt(N))
+    mcn = 64 if N >= 256 else 32
+    pos = O.pos_encoding_2d(h, h, C).reshape(N, C)
+    imgs = [_well_posed_image(N, C, G, k, mcn, pos, 1000 * (b + 1)) for b in range(B)]
+    feats = torch.stack([im[0] for im in imgs])
+    noise = torch.stack([im[1] for im in imgs])
+    x_pos, idx, score, down, numc, offs = ops.dpc_cluster(feats.to(DEV), noise.to(DEV), (h, h), k, 0.5, mcn, pos_table=pos.to(DEV))
+    assert torch.equal(x_pos.cpu(), feats + pos[None])
+    run = 0
+    undecidable = 0
+    for b in range(B):
+        o_down, o_idx, o_score = O.dpc_knn(feats[b] + pos, k, noise[b], 0.5, mcn)
+        m = imgs[b][2]
+        K = int(numc[b])
+        assert int(offs[b]) == run
+        run += K
+        assert K == o_down.numel() and torch.equal(down[b, :K].cpu(), o_down), f"image {b}: centres differ (margins {m})"
+        firm = m["token_gap"] > 2e-4
+        undecidable += int((~firm).sum())
+        assert torch.equal(idx[b].cpu()[firm], o_idx[firm]), f"image {b}: labels differ on well-separated tokens"
+        assert float((idx[b].cpu() == o_idx).float().mean()) > 0.98
+        torch.testing.assert_close(score[b].cpu(), o_score.reshape(-1), rtol=1e-3, atol=1e-5)
+    assert int(offs[B]) == run
+    assert undecidable <= 0.02 * B * N, f"{undecidable} tokens sit within 2e-4 of a tie"
+
+
+def test_dpc_internal_table_matches_reference_formula():
+    """setok_dpc_cluster (no table passed) builds the sincos table itself; it must agree with the reference's to 1 ulp."""
+    import ctypes as C_
+    from setok_b200 import _lib
+    B, h, C = 1, 16, 1024
+    N = h * h
+    feats = torch.zeros(B, N, C, device=DEV)
+    noise = torch.rand(B, N, device=DEV)
+    x_pos = torch.empty(B, N, C, device=DEV)
+    idx = torch.empty(B, N, dtype=torch.int64, device=DEV); down = torch.empty_like(idx)
+    score = torch.empty(B, N, device=DEV)
+    numc = torch.empty(B, dtype=torch.int32, device=DEV); offs = torch.empty(B + 1, dtype=torch.int32, device=DEV)
+    lib = _lib.load()
+    ws = torch.empty(lib.setok_dpc_workspace_bytes(B, N, C), dtype=torch.uint8, device=DEV)
+    st = lib.setok_dpc_cluster(feats.data_ptr(), 0, noise.data_ptr(), None, B, h, h, C, 16, 0.5, 64, x_pos.data_ptr(), idx.data_ptr(),
+                               score.data_ptr(), down.data_ptr(), numc.data_ptr(), offs.data_ptr(), ws.data_ptr(), ws.numel(),
+                               torch.cuda.current_stream().cuda_stream)
+    _lib.check(st, "setok_dpc_cluster")
+    torch.testing.assert_close(x_pos[0].cpu(), O.pos_encoding_2d(h, h, C).reshape(N, C), rtol=0, atol=2e-7)
+
+
+def test_dpc_properties_full_batch():
+    """BASELINE config 2 size (B=256, N=256, C=1024): structural invariants of the reference algorithm
+    (tokenizer.py:117-119): labels in [0,K), every centre owns its label, centres ascending, offsets = scan(K)."""
+    B, N, C = 256, 256, 1024
+    g = torch.Generator(device=DEV).manual_seed(3)
+    centres = torch.randn(B, 128, C, device=DEV, generator=g)
+    Gb = torch.randint(8, 129, (B,), device=DEV, generator=g)
+    lab = (torch.rand(B, N, device=DEV, generator=g) * Gb[:, None]).long()
+    feats = torch.gather(centres, 1, lab[..., None].expand(B, N, C)) + 0.05 * torch.randn(B, N, C, device=DEV, generator=g)
+    noise = torch.rand(B, N, device=DEV, generator=g)
+    x_pos, idx, score, down, numc, offs = ops.dpc_cluster(feats, noise, (16, 16), 16, 0.5, 64)
+    K = numc.long()
+    assert (K >= 1).all() and (K <= N).all()
+    assert (idx >= 0).all() and (idx < K[:, None]).all()
+    ar = torch.arange(N, device=DEV)[None]
+    valid = ar < K[:, None]
+    assert ((down >= 0) == valid).all()
+    d = down.clamp_min(0)
+    assert (torch.gather(idx, 1, d)[valid] == ar.expand(B, N)[valid]).all()          # centre c carries label c
+    assert ((d[:, 1:] > d[:, :-1]) | ~valid[:, 1:]).all()                            # ascending
+    assert torch.equal(offs.long(), torch.cat([torch.zeros(1, device=DEV, dtype=torch.long), K.cumsum(0)]))
+    assert len(set(K.tolist())) > 10, "dynamic K expected for mixture inputs"
+    # spot-check 4 images against the CPU oracle
+    pos = O.pos_encoding_2d(16, 16, C).reshape(N, C)
+    for b in (0, 85, 170, 255):
+        o_down, o_idx, _ = O.dpc_knn(feats[b].cpu() + pos, 16, noise[b].cpu(), 0.5, 64)
+        m = O.dpc_margins(feats[b].cpu() + pos, 16, noise[b].cpu(), 0.5, 64)
+        if m["threshold_margin"] > 2e-4:
+            firm = m["token_gap"] > 2e-4
+            assert torch.equal(down[b, :int(K[b])].cpu(), o_down) and torch.equal(idx[b].cpu()[firm], o_idx[firm])

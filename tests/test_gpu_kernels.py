@@ -1,0 +1,157 @@
+"""GPU parity: each CUDA primitive of libsetok_b200 (called through the C ABI) against torch fp32 on the
+same operands.  Tolerances: fp32 outputs 1e-4 of the output scale (identical bf16 operands, fp32
+accumulation: only summation order differs); bf16 outputs one bf16 ulp (2^-8 relative) on top."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():
+    pytest.skip("CUDA device required", allow_module_level=True)
+
+from setok_b200 import ops  # noqa: E402
+
+DEV = torch.device("cuda:0")
+
+
+def _close(got, ref, rel, what=""):
+    got, ref = got.float(), ref.float()
+    scale = ref.abs().max().clamp_min(1e-6)
+    err = (got - ref).abs().max() / scale
+    assert torch.isfinite(got).all(), f"{what}: non-finite output"
+    assert err <= rel, f"{what}: normalised max error {err:.3e} > {rel:.1e}"
+
+
+def _gemm_ref(a, w, bias, act, residual):
+    y = a.float() @ w.float().t()
+    if bias is not None:
+        y = y + bias
+    if act == ops.ACT_QUICK_GELU:
+        y = y * torch.sigmoid(1.702 * y)
+    elif act == ops.ACT_GELU_ERF:
+        y = torch.nn.functional.gelu(y)
+    if residual is not None:
+        y = y + residual.float()
+    return y
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (257, 1024, 1024), (1000, 3072, 1024), (514, 1024, 4096), (77, 64, 64),
+                                   (300, 48, 96), (1, 8, 8), (2056, 4096, 640), (129, 264, 72)])
+def test_gemm_shapes(M, N, K):
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
+    a = (torch.randn(M, K, generator=g)).to(DEV, torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) * K ** -0.5).to(DEV, torch.bfloat16)
+    bias = torch.randn(N, generator=g).to(DEV)
+    out = ops.gemm(a, w, bias, out_dtype=torch.float32)
+    _close(out, _gemm_ref(a, w, bias, 0, None), 1e-4, f"gemm f32 {M}x{N}x{K}")
+    out = ops.gemm(a, w, bias, out_dtype=torch.bfloat16)
+    _close(out, _gemm_ref(a, w, bias, 0, None), 5e-3, f"gemm bf16 {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("act", [ops.ACT_NONE, ops.ACT_QUICK_GELU, ops.ACT_GELU_ERF])
+@pytest.mark.parametrize("res", [None, torch.bfloat16, torch.float32])
+def test_gemm_epilogues(act, res):
+    M, N, K = 391, 520, 256
+    g = torch.Generator().manual_seed(5)
+    a = torch.randn(M, K, generator=g).to(DEV, torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) * K ** -0.5).to(DEV, torch.bfloat16)
+    bias = torch.randn(N, generator=g).to(DEV)
+    r = None if res is None else torch.randn(M, N, generator=g).to(DEV, res)
+    ref = _gemm_ref(a, w, bias, act, r)
+    _close(ops.gemm(a, w, bias, act=act, residual=r, out_dtype=torch.float32), ref, 1e-4, "epilogue f32")
+    _close(ops.gemm(a, w, None, act=act, residual=r, out_dtype=torch.float32), _gemm_ref(a, w, None, act, r), 1e-4, "no bias")
+    if r is not None:     # in place (the residual stream is updated in place on the product path)
+        out = r.clone()
+        ops.gemm(a, w, bias, act=act, residual=out, out=out)
+        _close(out, ref, 5e-3 if res == torch.bfloat16 else 1e-4, "in-place residual")
+
+
+def test_gemm_device_row_count_and_untouched_tail():
+    M, N, K = 1000, 256, 128
+    g = torch.Generator().manual_seed(9)
+    a = torch.randn(M, K, generator=g).to(DEV, torch.bfloat16)
+    w = torch.randn(N, K, generator=g).to(DEV, torch.bfloat16)
+    for live in (0, 1, 127, 128, 129, 777, 1000, 5000):
+        out = torch.full((M, N), -7.0, device=DEV)
+        m_dev = torch.tensor([live], dtype=torch.int32, device=DEV)
+        ops.gemm(a, w, None, out=out, m_dev=m_dev)
+        n = min(live, M)
+        _close(out[:n], _gemm_ref(a[:n], w, None, 0, None), 1e-4, f"m_dev={live}") if n else None
+        assert (out[n:] == -7.0).all(), f"rows past the live count were written (m_dev={live})"
+
+
+def test_gemm_linearity_full_size():
+    """Size-independent property at a BASELINE-size GEMM (65792 x 1024 x 1024): f(a1 + a2) == f(a1) + f(a2)."""
+    M, N, K = 65792, 1024, 1024
+    g = torch.Generator().manual_seed(1)
+    a1 = torch.randint(-4, 5, (M, K), generator=g).to(DEV, torch.bfloat16)     # small integers: exact in bf16 and fp32
+    a2 = torch.randint(-4, 5, (M, K), generator=g).to(DEV, torch.bfloat16)
+    w = torch.randint(-2, 3, (N, K), generator=g).to(DEV, torch.bfloat16)
+    y1 = ops.gemm(a1, w, out_dtype=torch.float32)
+    y2 = ops.gemm(a2, w, out_dtype=torch.float32)
+    y12 = ops.gemm((a1.float() + a2.float()).to(torch.bfloat16), w, out_dtype=torch.float32)
+    assert torch.equal(y12, y1 + y2)
+    rows = torch.randint(0, M, (64,), generator=g).to(DEV)
+    assert torch.equal(y1[rows], a1[rows].float() @ w.float().t())
+
+
+@pytest.mark.parametrize("rows,C", [(5, 64), (300, 768), (1000, 1024), (37, 4096), (16, 48)])
+@pytest.mark.parametrize("dt_in,dt_out", [(torch.float32, torch.bfloat16), (torch.bfloat16, torch.bfloat16), (torch.float32, torch.float32)])
+def test_layernorm(rows, C, dt_in, dt_out):
+    g = torch.Generator().manual_seed(rows + C)
+    x = (torch.randn(rows, C, generator=g) * 3 + 1).to(DEV, dt_in)
+    gamma = (1 + 0.1 * torch.randn(C, generator=g)).to(DEV)
+    beta = (0.1 * torch.randn(C, generator=g)).to(DEV)
+    ref = torch.nn.functional.layer_norm(x.float(), (C,), gamma, beta, 1e-5)
+    out = ops.layernorm(x, gamma, beta, 1e-5, out_dtype=dt_out)
+    _close(out, ref, 5e-3 if dt_out == torch.bfloat16 else 1e-5, "layernorm")
+    perm = torch.randperm(rows, generator=g).to(DEV, torch.int32)
+    out = ops.layernorm(x, gamma, beta, 1e-5, out_dtype=dt_out, gather=perm)
+    _close(out, ref[perm.long()], 5e-3 if dt_out == torch.bfloat16 else 1e-5, "layernorm gather")
+
+
+def _attn_ref(qkv, heads, scale, seg_off):
+    rows, C3 = qkv.shape
+    C = C3 // 3
+    hd = C // heads
+    q, k, v = qkv.float().split(C, dim=1)
+    out = torch.zeros(rows, C, device=qkv.device)
+    so = seg_off.tolist()
+    for s in range(len(so) - 1):
+        a, b = so[s], so[s + 1]
+        if a == b:
+            continue
+        for h in range(heads):
+            sl = slice(h * hd, (h + 1) * hd)
+            att = torch.softmax((q[a:b, sl] @ k[a:b, sl].t()) * scale, dim=-1)
+            out[a:b, sl] = att @ v[a:b, sl]
+    return out
+
+
+@pytest.mark.parametrize("C,heads", [(64, 2), (128, 2), (768, 2), (1024, 2), (64, 4)])
+def test_attention_ragged_segments(C, heads):
+    g = torch.Generator().manual_seed(C + heads)
+    lens = [1, 7, 130, 2, 33, 1, 64, 5]
+    so = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32)
+    rows = int(so[-1])
+    row_seg = torch.repeat_interleave(torch.arange(len(lens)), torch.tensor(lens)).to(torch.int32)
+    qkv = torch.randn(rows, 3 * C, generator=g).to(DEV, torch.bfloat16)
+    scale = (C // heads) ** -0.5
+    out = ops.attention(qkv, heads, scale, seg_off=so.to(DEV), row_seg=row_seg.to(DEV))
+    _close(out, _attn_ref(qkv, heads, scale, so), 6e-3, "ragged attention")
+    # device-side live row count: rows past it untouched by construction of the kernel loop
+    m_dev = torch.tensor([138], dtype=torch.int32, device=DEV)
+    out2 = ops.attention(qkv, heads, scale, seg_off=so.to(DEV), row_seg=row_seg.to(DEV), m_dev=m_dev)
+    assert torch.equal(out2[:138], out[:138])
+
+
+@pytest.mark.parametrize("T,B,heads", [(17, 3, 2), (64, 2, 4), (82, 2, 2), (197, 2, 12), (257, 3, 16), (577, 1, 16)])
+def test_attention_vit_hd64(T, B, heads):
+    C = heads * 64
+    g = torch.Generator().manual_seed(T)
+    qkv = torch.randn(B * T, 3 * C, generator=g).to(DEV, torch.bfloat16)
+    so = torch.arange(0, B * T + 1, T, dtype=torch.int32)
+    out = ops.attention(qkv, heads, 0.125, uniform_T=T)
+    _close(out, _attn_ref(qkv, heads, 0.125, so), 6e-3, "vit attention")

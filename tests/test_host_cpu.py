@@ -1,0 +1,94 @@
+"""CPU: host-side logic — the reference's plugin surface (ctor kwargs, state_dict keys, factory errors),
+the ragged container, sharding helpers."""
+import dataclasses
+
+import pytest
+import torch
+
+import setok_b200
+from setok_b200 import RaggedTokens, SetokTokenizer, build_vision_projector, build_vision_tower
+from setok_b200.dist import shard_batch
+from oracle import ref_loader
+
+VC = dict(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2, image_size=16, patch_size=4)
+
+
+def test_ctor_kwargs_and_extras_are_accepted():
+    tok = SetokTokenizer("siglip-x", hidden_dim=128, token_feat_dim=64, min_cluster_num=4, threshold=0.55, nheads=2,
+                         dim_feedforward=256, proj_drop=0.2, drop_path=0.0, inner_cluster_layers=1, intra_cluster_layers=3,
+                         attn_drop=0.0, pretrain_vision_tokenizer="", some_future_flag=1, vision_config=VC)
+    assert tok.inner_encoder.depth == 1 and tok.inter_encoder.depth == 3 and tok.threshold == 0.55
+    assert tok.is_loaded and tok.hidden_dim == 128 and tok.token_feat_dim == 64
+
+
+def test_state_dict_keys_match_reference_layout():
+    tok = SetokTokenizer("siglip-x", hidden_dim=128, token_feat_dim=64, min_cluster_num=4, dim_feedforward=256, vision_config=VC)
+    ours = {k for k in tok.state_dict() if not k.startswith("image_feature_encoder")}
+    expect = {"position_embedding.inv_freq", "out.weight", "out.bias"}
+    for enc in ("inner_encoder", "inter_encoder"):
+        for n in ("norm1", "norm2"):
+            expect |= {f"{enc}.{n}.weight", f"{enc}.{n}.bias"}
+        for i in range(2):
+            expect |= {f"{enc}.layers.{i}.0.weight", f"{enc}.layers.{i}.0.bias"}          # alias of norm1 (module.py:88)
+            for n in ("qkv", "proj"):
+                expect |= {f"{enc}.layers.{i}.1.{n}.weight", f"{enc}.layers.{i}.1.{n}.bias"}
+        for n in ("fc1", "fc2"):
+            expect |= {f"{enc}.mlp.{n}.weight", f"{enc}.mlp.{n}.bias"}
+    assert ours == expect
+    assert tok.inner_encoder.layers[0][0] is tok.inner_encoder.norm1
+    # xavier init / zero bias as tokenizer.py:59-72
+    assert float(tok.out.bias.abs().max()) == 0.0 and float(tok.inner_encoder.norm1.weight.min()) == 1.0
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present")
+def test_state_dict_keys_equal_the_live_reference():
+    ns = ref_loader.load_reference()
+    ref = ref_loader.build_reference_tokenizer(ns, None, hidden_dim=128, token_feat_dim=64, min_cluster_num=4, threshold=0.5, dim_feedforward=256)
+    tok = SetokTokenizer("siglip-x", hidden_dim=128, token_feat_dim=64, min_cluster_num=4, dim_feedforward=256, vision_config=VC)
+    rk = {k: tuple(v.shape) for k, v in ref.state_dict().items() if not k.startswith("image_feature_encoder")}
+    ok = {k: tuple(v.shape) for k, v in tok.state_dict().items() if not k.startswith("image_feature_encoder")}
+    assert rk == ok
+    tok.load_state_dict(ref.state_dict(), strict=False)
+    pr = ns.projector_builder.build_vision_projector("mlp2x_gelu_Norm", mm_hidden_size=64, hidden_size=128)
+    po = build_vision_projector("mlp2x_gelu_Norm", mm_hidden_size=64, hidden_size=128)
+    assert {k: tuple(v.shape) for k, v in pr.state_dict().items()} == {k: tuple(v.shape) for k, v in po.state_dict().items()}
+
+
+def test_factory_accepts_dataclass_dict_namespace_and_rejects_non_siglip():
+    @dataclasses.dataclass
+    class Args:
+        vision_tower: str = "google/siglip-so400m-patch14-384"
+        hidden_dim: int = 128
+        token_feat_dim: int = 64
+        min_cluster_num: int = 4
+        dim_feedforward: int = 256
+        pretrain_vision_tokenizer: str = ""
+    t1 = build_vision_tower(Args(), vision_config=VC)
+    t2 = build_vision_tower(dataclasses.asdict(Args()), vision_config=VC)
+    assert isinstance(t1, SetokTokenizer) and isinstance(t2, SetokTokenizer)
+    with pytest.raises(ValueError, match="Unknown vision tower"):
+        build_vision_tower(Args(vision_tower="openai/clip-vit-large-patch14"), vision_config=VC)
+    with pytest.raises(ValueError, match="Unknown projector type"):
+        build_vision_projector("resampler")
+
+
+def test_ragged_tokens_container():
+    data = torch.arange(40, dtype=torch.float32).reshape(10, 4)
+    rt = RaggedTokens(data, torch.tensor([0, 3, 3, 7], dtype=torch.int32))
+    assert len(rt) == 3 and rt.dim() == 3 and rt.counts == [3, 0, 4] and rt.total == 7
+    assert torch.equal(rt[0], data[:3]) and rt[1].shape == (0, 4) and torch.equal(rt[-1], data[3:7])
+    assert torch.equal(rt.packed(), data[:7])
+    pad, mask = rt.to_padded()
+    assert pad.shape == (3, 4, 4) and mask.sum().item() == 7 and torch.equal(pad[2], data[3:7])
+    assert [t.shape[0] for t in rt] == [3, 0, 4]
+    with pytest.raises(IndexError):
+        rt[3]
+
+
+def test_shard_batch_covers_everything_once():
+    for n in (1, 7, 64, 257):
+        for world in (1, 2, 3, 8):
+            spans = [shard_batch(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
