@@ -13,6 +13,9 @@
 // (m_dev) so data-dependent row counts need no host sync.
 #include "common.cuh"
 
+#include <mutex>
+#include <set>
+
 namespace setok {
 namespace {
 
@@ -40,6 +43,9 @@ struct GemmDev {
   int act, out_f32, res_kind, remap_P;
 };
 
+// Epilogue configuration is a template so the per-element code has no run-time branches; -1 = run time
+// (the generic instantiation serves the rarely used combinations).
+template <int ACT, int RES, int OUTF32, int REMAP>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmDev p) {
   extern __shared__ uint8_t smem_raw[];
@@ -119,21 +125,59 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
     }
   } else {
+    const int act = ACT >= 0 ? ACT : p.act;
+    const int res_kind = RES >= 0 ? RES : p.res_kind;
+    const bool out_f32 = OUTF32 >= 0 ? (OUTF32 != 0) : (p.out_f32 != 0);
+    const int remap_P = REMAP >= 0 ? (REMAP ? p.remap_P : 0) : p.remap_P;
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     uint8_t* stg = smem + OFF_STG + (warp - 2) * STG_BYTES_PER_WARP;
     int acc = 0; uint32_t acc_phase = 0;
     const int j = lane & 15;                      // 16-byte column chunk handled in the coalesced phase
+    const int rsub = lane >> 4;                   // row parity handled in the coalesced phase
+    const float* bias = p.bias;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m_blk = t / tiles_n, n_blk = t % tiles_n;
       const int row0 = m_blk * BM + q * 32;
       const int n0 = n_blk * BN;
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tcgen05_fence_after();
+      bool waited = false;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
 #pragma unroll 1
       for (int ch = 0; ch < BN / 64; ++ch) {
         const int gcol0 = n0 + ch * 64;
         if (gcol0 >= p.N) break;
+        const int col = gcol0 + 4 * j;
+        const bool col_ok = col < p.N;
+        // residual prefetch in the coalesced layout: in flight while the accumulator is drained and transposed
+        uint2 rb[16];
+        float4 rf[16];
+        if (res_kind == 1) {
+#pragma unroll
+          for (int it = 0; it < 16; ++it) {
+            const int grow = row0 + it * 2 + rsub;
+            rb[it] = make_uint2(0u, 0u);
+            if (grow < M_eff && col_ok) {
+              const long long rrow = remap_P > 0 ? (1 + grow % remap_P) : grow;
+              rb[it] = *reinterpret_cast<const uint2*>(static_cast<const bf16*>(p.res) + rrow * p.ldr + col);
+            }
+          }
+        } else if (res_kind == 2) {
+#pragma unroll
+          for (int it = 0; it < 16; ++it) {
+            const int grow = row0 + it * 2 + rsub;
+            rf[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (grow < M_eff && col_ok) {
+              const long long rrow = remap_P > 0 ? (1 + grow % remap_P) : grow;
+              rf[it] = *reinterpret_cast<const float4*>(static_cast<const float*>(p.res) + rrow * p.ldr + col);
+            }
+          }
+        }
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col_ok && bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(bias + col));
+        if (!waited) {
+          mbar_wait(tfull_bar(acc), acc_phase);
+          tcgen05_fence_after();
+          waited = true;
+        }
         uint32_t r0[32], r1[32];
         tmem_ld_32x32b_x32(taddr + ch * 64, r0);
         tmem_ld_32x32b_x32(taddr + ch * 64 + 32, r1);
@@ -147,33 +191,26 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
               make_uint4(r1[4 * c], r1[4 * c + 1], r1[4 * c + 2], r1[4 * c + 3]);
         }
         __syncwarp();
-        const int col = gcol0 + 4 * j;
-        const bool col_ok = col < p.N;
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (col_ok && p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-#pragma unroll 4
+#pragma unroll
         for (int it = 0; it < 16; ++it) {
-          const int r = it * 2 + (lane >> 4);
+          const int r = it * 2 + rsub;
           const int grow = row0 + r;
           float4 v = *reinterpret_cast<const float4*>(stg + r * 256 + ((j ^ (r & 7)) << 4));
+          v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+          if (act == SETOK_ACT_QUICK_GELU) {
+            v.x = act_quick_gelu(v.x); v.y = act_quick_gelu(v.y); v.z = act_quick_gelu(v.z); v.w = act_quick_gelu(v.w);
+          } else if (act == SETOK_ACT_GELU_ERF) {
+            v.x = act_gelu_erf(v.x); v.y = act_gelu_erf(v.y); v.z = act_gelu_erf(v.z); v.w = act_gelu_erf(v.w);
+          }
+          if (res_kind == 1) {
+            const float2 lo = unpack_bf16x2(rb[it].x), hi = unpack_bf16x2(rb[it].y);
+            v.x += lo.x; v.y += lo.y; v.z += hi.x; v.w += hi.y;
+          } else if (res_kind == 2) {
+            v.x += rf[it].x; v.y += rf[it].y; v.z += rf[it].z; v.w += rf[it].w;
+          }
           if (grow < M_eff && col_ok) {
-            v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-            if (p.act == SETOK_ACT_QUICK_GELU) {
-              v.x = act_quick_gelu(v.x); v.y = act_quick_gelu(v.y); v.z = act_quick_gelu(v.z); v.w = act_quick_gelu(v.w);
-            } else if (p.act == SETOK_ACT_GELU_ERF) {
-              v.x = act_gelu_erf(v.x); v.y = act_gelu_erf(v.y); v.z = act_gelu_erf(v.z); v.w = act_gelu_erf(v.w);
-            }
-            long long orow = grow, rrow = grow;
-            if (p.remap_P > 0) { orow = grow + grow / p.remap_P + 1; rrow = 1 + grow % p.remap_P; }
-            if (p.res_kind == 1) {
-              const uint2 u = *reinterpret_cast<const uint2*>(static_cast<const bf16*>(p.res) + rrow * p.ldr + col);
-              const float2 lo = unpack_bf16x2(u.x), hi = unpack_bf16x2(u.y);
-              v.x += lo.x; v.y += lo.y; v.z += hi.x; v.w += hi.y;
-            } else if (p.res_kind == 2) {
-              const float4 rr = *reinterpret_cast<const float4*>(static_cast<const float*>(p.res) + rrow * p.ldr + col);
-              v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
-            }
-            if (p.out_f32) {
+            const long long orow = remap_P > 0 ? (grow + grow / remap_P + 1) : grow;
+            if (out_f32) {
               *reinterpret_cast<float4*>(static_cast<float*>(p.D) + orow * p.ldd + col) = v;
             } else {
               *reinterpret_cast<uint2*>(static_cast<bf16*>(p.D) + orow * p.ldd + col) =
@@ -183,6 +220,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
         __syncwarp();
       }
+      if (!waited) { mbar_wait(tfull_bar(acc), acc_phase); tcgen05_fence_after(); }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -249,10 +287,29 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   }
   if (g.bias) SETOK_REQUIRE(aligned16(g.bias), SETOK_ERR_BAD_ARG, "gemm: bias must be 16-byte aligned");
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    SETOK_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
+  using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, GemmDev);
+  const int res_kind = g.residual ? (g.residual_dtype == SETOK_BF16 ? 1 : 2) : 0;
+  const int out_f32 = g.out_dtype == SETOK_F32 ? 1 : 0;
+  // specialised epilogues for the combinations the tokenizer path launches; everything else -> generic
+  KernelFn fn = gemm_bf16_tcgen05_kernel<-1, -1, -1, -1>;
+  if (g.remap_P == 0) {
+    if (g.act == SETOK_ACT_NONE && res_kind == 0 && !out_f32) fn = gemm_bf16_tcgen05_kernel<0, 0, 0, 0>;              // qkv
+    else if (g.act == SETOK_ACT_NONE && res_kind == 1 && !out_f32) fn = gemm_bf16_tcgen05_kernel<0, 1, 0, 0>;         // ViT out_proj / fc2
+    else if (g.act == SETOK_ACT_QUICK_GELU && res_kind == 0 && !out_f32) fn = gemm_bf16_tcgen05_kernel<1, 0, 0, 0>;   // ViT fc1
+    else if (g.act == SETOK_ACT_GELU_ERF && res_kind == 0 && !out_f32) fn = gemm_bf16_tcgen05_kernel<2, 0, 0, 0>;     // head / projector fc1
+    else if (g.act == SETOK_ACT_NONE && res_kind == 2 && out_f32) fn = gemm_bf16_tcgen05_kernel<0, 2, 1, 0>;          // head proj / fc2
+    else if (g.act == SETOK_ACT_NONE && res_kind == 0 && out_f32) fn = gemm_bf16_tcgen05_kernel<0, 0, 1, 0>;          // out / projector last
+  } else if (g.act == SETOK_ACT_NONE && res_kind == 2 && out_f32) {
+    fn = gemm_bf16_tcgen05_kernel<0, 2, 1, 1>;                                                                         // patch embedding
+  }
+  static std::mutex attr_mu;
+  static std::set<KernelFn> attr_done;
+  {
+    std::lock_guard<std::mutex> lk(attr_mu);
+    if (!attr_done.count(fn)) {
+      SETOK_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      attr_done.insert(fn);
+    }
   }
   CUtensorMap tmA, tmB;
   SETOK_TRY(make_tmap_2d_bf16(&tmA, g.A, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)g.lda, BM));
@@ -260,11 +317,11 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   GemmDev p;
   p.D = g.D; p.ldd = g.ldd; p.bias = g.bias; p.res = g.residual; p.ldr = g.ldr; p.m_dev = g.m_dev;
   p.M = g.M; p.N = g.N; p.K = g.K; p.act = g.act; p.out_f32 = g.out_dtype == SETOK_F32;
-  p.res_kind = g.residual ? (g.residual_dtype == SETOK_BF16 ? 1 : 2) : 0;
+  p.res_kind = res_kind;
   p.remap_P = g.remap_P;
   const int tiles = ceil_div(g.M, BM) * ceil_div(g.N, BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_bf16_tcgen05_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
+  fn<<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
   SETOK_LAUNCH_CHECK();
   return SETOK_OK;
 }
