@@ -2,11 +2,13 @@
 //
 //   D[M,N] = epilogue(A[M,K] * W[N,K]^T),  fp32 accumulation in TMEM.
 //
-// One CTA per SM, 192 threads:
+// One CTA per SM, 320 threads:
 //   warp 0      TMA producer   (cp.async.bulk.tensor 2-D, 128B swizzle, 4-stage mbarrier ring)
 //   warp 1      MMA issuer     (one thread: tcgen05.mma.cta_group::1.kind::f16, 128x256x16 per instr),
 //               owns the TMEM allocation (512 columns = two 128x256 fp32 accumulators)
-//   warps 2..5  epilogue       (tcgen05.ld -> per-warp smem transpose -> coalesced bias/act/residual/store)
+//   warps 2..9  epilogue       (tcgen05.ld -> per-warp smem transpose -> coalesced bias/act/residual/store);
+//               two warps per TMEM lane quarter (one per 128-column half) so each SM sub-partition has two
+//               epilogue warps to hide the MUFU / residual-load latency behind
 // The two accumulators let the epilogue of tile i overlap the MMAs of tile i+1.  Tiles are walked
 // N-fastest so the CTAs running concurrently share A row-blocks through L2 while W (<= 8 MB) stays
 // L2-resident.  M may be ragged (TMA zero-fills / the epilogue masks) and may live on the device
@@ -23,15 +25,15 @@ constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KiB
 constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KiB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int EPI_WARPS = 4;
-constexpr int STG_BYTES_PER_WARP = 32 * 64 * 4;   // 32 rows x 64 fp32 columns
+constexpr int EPI_WARPS = 8;                      // two warps per TMEM lane quarter, each owning half of the 256 columns
+constexpr int STG_BYTES_PER_WARP = 32 * 32 * 4;   // 32 rows x 32 fp32 columns
 constexpr int OFF_A = 0;
 constexpr int OFF_B = STAGES * A_STAGE_BYTES;
 constexpr int OFF_STG = OFF_B + STAGES * B_STAGE_BYTES;
 constexpr int OFF_BAR = OFF_STG + EPI_WARPS * STG_BYTES_PER_WARP;
 constexpr int NUM_BARS = 2 * STAGES + 4;
 constexpr int SMEM_BYTES = OFF_BAR + NUM_BARS * 8 + 16 + 1024;   // + tmem ptr + alignment slack
-constexpr int THREADS = 192;
+constexpr int THREADS = 64 + 32 * EPI_WARPS;
 constexpr int TMEM_COLS = 512;
 
 struct GemmDev {
@@ -130,30 +132,31 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const bool out_f32 = OUTF32 >= 0 ? (OUTF32 != 0) : (p.out_f32 != 0);
     const int remap_P = REMAP >= 0 ? (REMAP ? p.remap_P : 0) : p.remap_P;
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;             // which 128-column half of the tile this warp drains
     uint8_t* stg = smem + OFF_STG + (warp - 2) * STG_BYTES_PER_WARP;
     int acc = 0; uint32_t acc_phase = 0;
-    const int j = lane & 15;                      // 16-byte column chunk handled in the coalesced phase
-    const int rsub = lane >> 4;                   // row parity handled in the coalesced phase
+    const int j = lane & 7;                       // 16-byte column chunk handled in the coalesced phase
+    const int rsub = lane >> 3;                   // row (mod 4) handled in the coalesced phase
     const float* bias = p.bias;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m_blk = t / tiles_n, n_blk = t % tiles_n;
       const int row0 = m_blk * BM + q * 32;
-      const int n0 = n_blk * BN;
+      const int n0 = n_blk * BN + half * 128;
       bool waited = false;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + half * 128);
 #pragma unroll 1
-      for (int ch = 0; ch < BN / 64; ++ch) {
-        const int gcol0 = n0 + ch * 64;
+      for (int ch = 0; ch < 4; ++ch) {
+        const int gcol0 = n0 + ch * 32;
         if (gcol0 >= p.N) break;
         const int col = gcol0 + 4 * j;
         const bool col_ok = col < p.N;
         // residual prefetch in the coalesced layout: in flight while the accumulator is drained and transposed
-        uint2 rb[16];
-        float4 rf[16];
+        uint2 rb[8];
+        float4 rf[8];
         if (res_kind == 1) {
 #pragma unroll
-          for (int it = 0; it < 16; ++it) {
-            const int grow = row0 + it * 2 + rsub;
+          for (int it = 0; it < 8; ++it) {
+            const int grow = row0 + it * 4 + rsub;
             rb[it] = make_uint2(0u, 0u);
             if (grow < M_eff && col_ok) {
               const long long rrow = remap_P > 0 ? (1 + grow % remap_P) : grow;
@@ -162,8 +165,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
         } else if (res_kind == 2) {
 #pragma unroll
-          for (int it = 0; it < 16; ++it) {
-            const int grow = row0 + it * 2 + rsub;
+          for (int it = 0; it < 8; ++it) {
+            const int grow = row0 + it * 4 + rsub;
             rf[it] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (grow < M_eff && col_ok) {
               const long long rrow = remap_P > 0 ? (1 + grow % remap_P) : grow;
@@ -178,24 +181,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           tcgen05_fence_after();
           waited = true;
         }
-        uint32_t r0[32], r1[32];
-        tmem_ld_32x32b_x32(taddr + ch * 64, r0);
-        tmem_ld_32x32b_x32(taddr + ch * 64 + 32, r1);
+        uint32_t r0[32];
+        tmem_ld_32x32b_x32(taddr + ch * 32, r0);
         tmem_ld_wait();
-        // transpose through smem: thread `lane` owns tile row q*32+lane, 64 fp32 columns
+        // transpose through smem: thread `lane` owns tile row q*32+lane, 32 fp32 columns (8 x 16 B, XOR-swizzled)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          *reinterpret_cast<uint4*>(stg + lane * 256 + ((c ^ (lane & 7)) << 4)) =
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) =
               make_uint4(r0[4 * c], r0[4 * c + 1], r0[4 * c + 2], r0[4 * c + 3]);
-          *reinterpret_cast<uint4*>(stg + lane * 256 + (((c + 8) ^ (lane & 7)) << 4)) =
-              make_uint4(r1[4 * c], r1[4 * c + 1], r1[4 * c + 2], r1[4 * c + 3]);
-        }
         __syncwarp();
 #pragma unroll
-        for (int it = 0; it < 16; ++it) {
-          const int r = it * 2 + rsub;
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + rsub;
           const int grow = row0 + r;
-          float4 v = *reinterpret_cast<const float4*>(stg + r * 256 + ((j ^ (r & 7)) << 4));
+          float4 v = *reinterpret_cast<const float4*>(stg + r * 128 + ((j ^ (r & 7)) << 4));
           v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
           if (act == SETOK_ACT_QUICK_GELU) {
             v.x = act_quick_gelu(v.x); v.y = act_quick_gelu(v.y); v.z = act_quick_gelu(v.z); v.w = act_quick_gelu(v.w);
