@@ -1,10 +1,9 @@
 // attention.cu — self-attention over packed rows.
 //
 // Two kernels, chosen by shape (not by backend):
-//  * attn_mma_hd64_kernel: uniform-length segments (the ViT: T = N+1 rows per image), head_dim 64.
-//    Flash-style single pass, bf16 warp MMA with fp32 softmax statistics, K/V chunks staged in
-//    XOR-swizzled shared memory.  (Round-1 implementation; the tcgen05/TMEM version replaces it.)
-//  * attn_seg_kernel: arbitrary ragged segments (clusters of 1..N tokens, images of K_b tokens),
+//  * attn_tcgen05_hd64_kernel (attention_tcgen05.cu): uniform-length segments (the ViT: T = N+1 rows per
+//    image), head_dim 64, on the tensor cores with S/O in TMEM.
+//  * attn_seg_kernel (here): arbitrary ragged segments (clusters of 1..N tokens, images of K_b tokens),
 //    head_dim up to 512 (the head uses 2 heads of C/2).  One warp per (row, head), online softmax,
 //    16-byte coalesced K/V row reads; fp32 math throughout.  The work is tiny (8*C*sum n_g^2 FLOPs)
 //    and irregular, so it stays on CUDA cores by design.
@@ -123,150 +122,6 @@ __global__ void __launch_bounds__(256) attn_seg_kernel(const bf16* __restrict__ 
   }
 }
 
-// -------------------------------------------------------------------------------------------------
-// uniform segments of T rows, head_dim 64
-// -------------------------------------------------------------------------------------------------
-constexpr int AQ = 64, AK = 64, HD = 64;
-
-__device__ __forceinline__ uint32_t sw_off(int row, int chunk) {   // byte offset in a [rows][64 bf16] swizzled tile
-  return static_cast<uint32_t>(row * 128 + ((chunk ^ (row & 7)) << 4));
-}
-
-__device__ __forceinline__ void load_tile_64x64(bf16* s, const bf16* g, long long ld, int row0, int row_end, int tid) {
-  // 64 rows x 8 chunks of 16 B; rows >= row_end are zero-filled
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int idx = tid + i * 128;
-    const int row = idx >> 3, c = idx & 7;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (row0 + row < row_end) v = *reinterpret_cast<const uint4*>(g + (row0 + row) * ld + c * 8);
-    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(s) + sw_off(row, c)) = v;
-  }
-}
-
-__global__ void __launch_bounds__(128) attn_mma_hd64_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, int heads,
-                                                            int C, float scale_log2) {
-  __shared__ __align__(128) bf16 sQ[AQ * HD];
-  __shared__ __align__(128) bf16 sK[AK * HD];
-  __shared__ __align__(128) bf16 sV[AK * HD];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const long long ld = 3LL * C;
-  const long long img_row0 = static_cast<long long>(b) * T;
-  const bf16* gq = qkv + img_row0 * ld + h * HD;
-  const bf16* gk = gq + C;
-  const bf16* gv = gq + 2 * C;
-
-  load_tile_64x64(sQ, gq, ld, qt * AQ, T, tid);
-  __syncthreads();
-  const bool active = qt * AQ + warp * 16 < T;
-  uint32_t qf[4][4];
-  {
-    const uint32_t qbase = smem_u32(sQ);
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      const int row = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-      const int chunk = ks * 2 + (lane >> 4);
-      ldmatrix_x4(qbase + sw_off(row, chunk), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
-    }
-  }
-  float o[8][4];
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int e = 0; e < 4; ++e) o[i][e] = 0.f;
-  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-  const uint32_t kbase = smem_u32(sK), vbase = smem_u32(sV);
-  const int nchunks = (T + AK - 1) / AK;
-  for (int kc = 0; kc < nchunks; ++kc) {
-    __syncthreads();
-    load_tile_64x64(sK, gk, ld, kc * AK, T, tid);
-    load_tile_64x64(sV, gv, ld, kc * AK, T, tid);
-    __syncthreads();
-    if (!active) continue;
-    const int valid = min(AK, T - kc * AK);
-    const int nkg = (valid + 15) >> 4;
-    float s[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) s[i][e] = 0.f;
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      if (g < nkg) {
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const int mi = lane >> 3;
-          const int row = g * 16 + (mi >> 1) * 8 + (lane & 7);
-          const int chunk = ks * 2 + (mi & 1);
-          uint32_t b0, b1, b2, b3;
-          ldmatrix_x4(kbase + sw_off(row, chunk), b0, b1, b2, b3);
-          mma_bf16_16816(s[2 * g], qf[ks], b0, b1);
-          mma_bf16_16816(s[2 * g + 1], qf[ks], b2, b3);
-        }
-      }
-    }
-    // mask + running max
-    float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int key = nt * 8 + 2 * (lane & 3) + (e & 1);
-        const float v = key < valid ? s[nt][e] * scale_log2 : -INFINITY;
-        s[nt][e] = v;
-        if (e < 2) mx0 = fmaxf(mx0, v); else mx1 = fmaxf(mx1, v);
-      }
-    }
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
-    const float a0 = exp2f(m0 - mn0), a1 = exp2f(m1 - mn1);
-    m0 = mn0; m1 = mn1;
-    float ps0 = 0.f, ps1 = 0.f;
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      s[nt][0] = exp2f(s[nt][0] - mn0); s[nt][1] = exp2f(s[nt][1] - mn0);
-      s[nt][2] = exp2f(s[nt][2] - mn1); s[nt][3] = exp2f(s[nt][3] - mn1);
-      ps0 += s[nt][0] + s[nt][1]; ps1 += s[nt][2] + s[nt][3];
-    }
-    l0 = l0 * a0 + ps0; l1 = l1 * a1 + ps1;
-#pragma unroll
-    for (int dt = 0; dt < 8; ++dt) { o[dt][0] *= a0; o[dt][1] *= a0; o[dt][2] *= a1; o[dt][3] *= a1; }
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      if (g < nkg) {
-        uint32_t pa[4];
-        pa[0] = pack_bf16x2(s[2 * g][0], s[2 * g][1]);
-        pa[1] = pack_bf16x2(s[2 * g][2], s[2 * g][3]);
-        pa[2] = pack_bf16x2(s[2 * g + 1][0], s[2 * g + 1][1]);
-        pa[3] = pack_bf16x2(s[2 * g + 1][2], s[2 * g + 1][3]);
-#pragma unroll
-        for (int d2 = 0; d2 < 4; ++d2) {
-          const int mi = lane >> 3;
-          const int row = g * 16 + (mi & 1) * 8 + (lane & 7);
-          const int chunk = 2 * d2 + (mi >> 1);
-          uint32_t b0, b1, b2, b3;
-          ldmatrix_x4_trans(vbase + sw_off(row, chunk), b0, b1, b2, b3);
-          mma_bf16_16816(o[2 * d2], pa, b0, b1);
-          mma_bf16_16816(o[2 * d2 + 1], pa, b2, b3);
-        }
-      }
-    }
-  }
-  if (!active) return;
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
-  const int r0 = qt * AQ + warp * 16 + (lane >> 2), r1 = r0 + 8;
-#pragma unroll
-  for (int dt = 0; dt < 8; ++dt) {
-    const int col = h * HD + dt * 8 + 2 * (lane & 3);
-    if (r0 < T) *reinterpret_cast<uint32_t*>(out + (img_row0 + r0) * C + col) = pack_bf16x2(o[dt][0] * i0, o[dt][1] * i0);
-    if (r1 < T) *reinterpret_cast<uint32_t*>(out + (img_row0 + r1) * C + col) = pack_bf16x2(o[dt][2] * i1, o[dt][3] * i1);
-  }
-}
-
 }  // namespace
 
 int launch_attention(const void* qkv, void* out, int rows, int C, int heads, float scale, const int32_t* seg_off,
@@ -281,13 +136,8 @@ int launch_attention(const void* qkv, void* out, int rows, int C, int heads, flo
   } else {
     SETOK_REQUIRE(seg_off && row_seg, SETOK_ERR_BAD_ARG, "attention: seg_off/row_seg required for ragged segments");
   }
-  if (uniform_T > 0 && hd == HD && m_dev == nullptr) {
-    const float scale_log2 = scale * 1.4426950408889634f;
-    dim3 grid(ceil_div(uniform_T, AQ), heads, rows / uniform_T);
-    attn_mma_hd64_kernel<<<grid, 128, 0, stream>>>(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), uniform_T, heads, C, scale_log2);
-    SETOK_LAUNCH_CHECK();
-    return SETOK_OK;
-  }
+  if (uniform_T > 0 && hd == 64 && m_dev == nullptr)
+    return launch_attention_tcgen05(qkv, out, rows / uniform_T, uniform_T, C, heads, scale, stream);
   const long long warps = static_cast<long long>(rows) * heads;
   long long blocks = (warps + 7) / 8;
   const long long cap = static_cast<long long>(num_sms()) * 32;
