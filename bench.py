@@ -40,6 +40,9 @@ HEAD = dict(hidden_dim=1024, token_feat_dim=1024, min_cluster_num=64, threshold=
             inner_cluster_layers=2, intra_cluster_layers=2, mm_vision_select_layer=-2)
 KNN_K = 16
 BATCH = 256
+# dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch, mean of fc2/qkv/out_proj/fc1 (profiles/r01_ncu_summary.md)
+NCU_GEMM_DRAM_BYTES_PER_LAUNCH = (804.5e6 + 494.0e6 + 363.0e6 + 631.8e6) / 4
+NCU_CLUSTER_DRAM_BYTES_PER_LAUNCH = (269.5e6 + 221.7e6) + (269.4e6 + 51.0e6) + (67.5e6 + 1.5e6)   # posadd + gram + select
 
 
 def peaks():
@@ -331,12 +334,13 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {"kernel": "gemm_bf16_tcgen05_kernel (ViT layer launch mix: qkv/out_proj/fc1/fc2 at M=65792)", "bound": "tensor",
                      "achieved": gemm_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": gemm_tf / pk["tf_sustained"],
-                     "traffic": None, "flops_per_launch": gemm_flops, "ms_per_launch": gemm_ms,
+                     "traffic": NCU_GEMM_DRAM_BYTES_PER_LAUNCH, "traffic_source": "ncu --set full dram__bytes_read+write, mean over the 4 shapes (profiles/r01_ncu_summary.md); algorithmic operand bytes are 607e6",
+                     "flops_per_launch": gemm_flops, "ms_per_launch": gemm_ms,
                      "peak_source": f"{pk['src']} sustained bf16 (kernel timed inside a long loop)",
                      "step_share": (4 * layers_run * gemm_ms) / step_ms,
                      "vit_tensor_frac_of_step": (BATCH * vit_flops_per_image(layers_run) / (step_ms * 1e-3) / 1e12) / pk["tf_sustained"]},
         "roofline_cluster": {"kernel": "posadd_sqnorm + gram_dist + dpc_select (a3+a4), B=256 N=256 C=1024 feature-injected", "bound": "hbm",
-                             "achieved": cl_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": cl_gbs / pk["hbm"], "traffic": None,
+                             "achieved": cl_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": cl_gbs / pk["hbm"], "traffic": NCU_CLUSTER_DRAM_BYTES_PER_LAUNCH,
                              "bytes_per_launch": cl_bytes, "ms_per_launch": cl_ms, "k_min_mean_max": kstats,
                              "tensor_frac_if_compute": (BATCH * 2.0 * 256 * 256 * 1024 / (cl_ms * 1e-3) / 1e12) / pk["tf_burst"]},
     }

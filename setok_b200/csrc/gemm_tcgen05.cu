@@ -146,7 +146,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const int n0 = n_blk * BN + half * 128;
       bool waited = false;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + half * 128);
-#pragma unroll 1
+      // bf16 residual (the ViT's out_proj / fc2): the whole tile's residual is requested before waiting for the
+      // accumulator, so the HBM latency overlaps the MMAs instead of being paid once per 32-column chunk
+      constexpr bool kTilePrefetch = (RES == 1);
+      uint2 rt[4][8];
+      if (kTilePrefetch) {
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const int col = n0 + ch * 32 + 4 * j;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int grow = row0 + it * 4 + rsub;
+            rt[ch][it] = make_uint2(0u, 0u);
+            if (grow < M_eff && col < p.N)
+              rt[ch][it] = *reinterpret_cast<const uint2*>(static_cast<const bf16*>(p.res) + static_cast<long long>(grow) * p.ldr + col);
+          }
+        }
+      }
+#pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
         const int gcol0 = n0 + ch * 32;
         if (gcol0 >= p.N) break;
@@ -155,7 +172,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         // residual prefetch in the coalesced layout: in flight while the accumulator is drained and transposed
         uint2 rb[8];
         float4 rf[8];
-        if (res_kind == 1) {
+        if (kTilePrefetch) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) rb[it] = rt[ch][it];
+        } else if (res_kind == 1) {
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int grow = row0 + it * 4 + rsub;
