@@ -105,44 +105,49 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle port on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_oracle_rate(n_images: int, seed: int = 1234, warm: bool = True):
-    """Runs the oracle (reference algorithm, fp32, torch CPU, per-image head loop as the reference does) on
-    `n_images` Mondrian images; returns (images/s, seconds, stage dict)."""
-    from oracle import setok_oracle as O
-    from setok_b200.synth import mondrian_images
-    torch.set_num_threads(os.cpu_count() or 1)
-    C = VIT["hidden_size"]
-    tp = O.make_tower_params(C, VIT["num_hidden_layers"], VIT["num_attention_heads"], VIT["patch_size"], VIT["image_size"], seed=0)
-    hp = O.make_head_params(C, HEAD["token_feat_dim"], HEAD["dim_feedforward"], seed=0)
-    imgs = mondrian_images(n_images, 224, seed, "cpu")
-    noise = torch.rand(n_images, 256, generator=torch.Generator().manual_seed(seed))
-    kw = dict(patch=14, heads=16, layers=24, select_layer=-2)
-    with torch.no_grad():
-        if warm:
-            O.setok_forward(imgs[:1], noise[:1], tp, hp, min_cluster_num=64, threshold=0.5, k=KNN_K, **kw)
-        t0 = time.perf_counter()
-        feats = O.tower_features(imgs, tp, **kw)
-        t1 = time.perf_counter()
-        O.setok_forward(imgs, noise, tp, hp, min_cluster_num=64, threshold=0.5, k=KNN_K, feats=feats, **kw)
-        t2 = time.perf_counter()
-    return n_images / (t2 - t0), t2 - t0, {"vit_s": t1 - t0, "head_s": t2 - t1}
+class CpuOracle:
+    """The oracle port of the reference (fp32, torch CPU, per-image head loop exactly as the reference does) with the
+    bench model's seeded weights.  Built once; `run(n)` times one forward over `n` Mondrian images."""
+
+    def __init__(self, max_images: int, seed: int = 1234):
+        from oracle import setok_oracle as O
+        from setok_b200.synth import mondrian_images
+        self.O = O
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        C = VIT["hidden_size"]
+        self.tp = O.make_tower_params(C, VIT["num_hidden_layers"], VIT["num_attention_heads"], VIT["patch_size"], VIT["image_size"], seed=0)
+        self.hp = O.make_head_params(C, HEAD["token_feat_dim"], HEAD["dim_feedforward"], seed=0)
+        self.imgs = mondrian_images(max_images, 224, seed, "cpu")
+        self.noise = torch.rand(max_images, 256, generator=torch.Generator().manual_seed(seed))
+        self.kw = dict(patch=14, heads=16, layers=24, select_layer=-2)
+
+    def run(self, n: int):
+        O = self.O
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            feats = O.tower_features(self.imgs[:n], self.tp, **self.kw)
+            t1 = time.perf_counter()
+            O.setok_forward(self.imgs[:n], self.noise[:n], self.tp, self.hp, min_cluster_num=64, threshold=0.5, k=KNN_K, feats=feats, **self.kw)
+            t2 = time.perf_counter()
+        return t2 - t0, {"vit_s": t1 - t0, "head_s": t2 - t1}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    _, t1, _ = cpu_oracle_rate(1, warm=False)                       # sizes the bounded sample
+    orc = CpuOracle(8)
+    t1, _ = orc.run(1)                                              # warms up and sizes the bounded sample
     budget = 150.0
     n = int(max(1, min(8, budget / max((args.steps + args.warmup) * t1, 1e-3))))
     for _ in range(args.warmup):
-        cpu_oracle_rate(n, warm=False)
-    t0 = time.perf_counter()
+        orc.run(n)
+    dt = 0.0
     for _ in range(args.steps):
-        cpu_oracle_rate(n, warm=False)
-    dt = time.perf_counter() - t0
+        dt += orc.run(n)[0]
     v = args.steps * n / dt
+    cores = orc.cores
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args.gpus, sample=n),
@@ -346,8 +351,11 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu:
         n = args.cpu_sample
-        v, secs, stages = cpu_oracle_rate(n)
-        cores = os.cpu_count() or 1
+        orc = CpuOracle(n)
+        orc.run(1)
+        secs, stages = orc.run(n)
+        v = n / secs
+        cores = orc.cores
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{n} of the 256 images (same generator), oracle port of the reference, torch CPU fp32, "
                                           f"{cores} threads: ViT {stages['vit_s']:.1f}s + per-image head loop {stages['head_s']:.1f}s"}
