@@ -2,7 +2,7 @@
 //
 //   D[M,N] = epilogue(A[M,K] * W[N,K]^T),  fp32 accumulation in TMEM.
 //
-// One CTA per SM, 320 threads:
+// One CTA per SM (CTAs paired into 2-CTA clusters for the cta_group::2 variant, see Cfg), 320 threads:
 //   warp 8      TMA producer   (cp.async.bulk.tensor 2-D, 128B swizzle, 4-stage mbarrier ring)
 //   warp 9      MMA issuer     (one thread: tcgen05.mma.cta_group::1.kind::f16, 128x256x16 per instr),
 //               owns the TMEM allocation (512 columns = two 128x256 fp32 accumulators); highest warp id
@@ -22,20 +22,28 @@
 namespace setok {
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UMMA_K = 16;
-constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KiB
-constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KiB
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16;
 constexpr int EPI_WARPS = 8;                      // two warps per TMEM lane quarter, each owning half of the 256 columns
 constexpr int STG_BYTES_PER_WARP = 32 * 32 * 4;   // 32 rows x 32 fp32 columns
-constexpr int OFF_A = 0;
-constexpr int OFF_B = STAGES * A_STAGE_BYTES;
-constexpr int OFF_STG = OFF_B + STAGES * B_STAGE_BYTES;
-constexpr int OFF_BAR = OFF_STG + EPI_WARPS * STG_BYTES_PER_WARP;
-constexpr int NUM_BARS = 2 * STAGES + 4;
-constexpr int SMEM_BYTES = OFF_BAR + NUM_BARS * 8 + 16 + 1024;   // + tmem ptr + alignment slack
 constexpr int THREADS = 64 + 32 * EPI_WARPS;
 constexpr int TMEM_COLS = 512;
+constexpr int A_STAGE_BYTES = BM * BK * 2;        // 16 KiB: this CTA's 128 rows of A
+
+// CG = 1: one CTA computes a 128x256 tile, B tile 256 rows (32 KiB/stage), 4 stages.
+// CG = 2: a CTA pair (cta_group::2) computes a 256x256 tile; each CTA stages its own 128 rows of A and HALF of the B
+//         tile (128 rows, 16 KiB/stage) -- the tensor cores read the other half from the peer's shared memory -- so
+//         the B operand crosses L2->SM once per pair, and the smaller stage buys 6 stages.
+template <int CG> struct Cfg {
+  static constexpr int STAGES = CG == 2 ? 6 : 4;
+  static constexpr int B_STAGE_BYTES = (BN / CG) * BK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int OFF_A = 0;
+  static constexpr int OFF_B = STAGES * A_STAGE_BYTES;
+  static constexpr int OFF_STG = OFF_B + STAGES * B_STAGE_BYTES;
+  static constexpr int OFF_BAR = OFF_STG + EPI_WARPS * STG_BYTES_PER_WARP;
+  static constexpr int NUM_BARS = 2 * STAGES + 4;
+  static constexpr int SMEM_BYTES = OFF_BAR + NUM_BARS * 8 + 16 + 1024;   // + tmem ptr + alignment slack
+};
 
 struct GemmDev {
   void* D; long long ldd;
@@ -48,9 +56,13 @@ struct GemmDev {
 
 // Epilogue configuration is a template so the per-element code has no run-time branches; -1 = run time
 // (the generic instantiation serves the rarely used combinations).
-template <int ACT, int RES, int OUTF32, int REMAP>
+template <int CG, int ACT, int RES, int OUTF32, int REMAP>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmDev p) {
+  constexpr int STAGES = Cfg<CG>::STAGES, B_STAGE_BYTES = Cfg<CG>::B_STAGE_BYTES, STAGE_BYTES = Cfg<CG>::STAGE_BYTES;
+  constexpr int OFF_A = Cfg<CG>::OFF_A, OFF_B = Cfg<CG>::OFF_B, OFF_STG = Cfg<CG>::OFF_STG, OFF_BAR = Cfg<CG>::OFF_BAR;
+  constexpr int NUM_BARS = Cfg<CG>::NUM_BARS;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;      // position in the CTA pair; rank 0 issues the MMAs
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -70,43 +82,59 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   if (warp == W_TMA && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    // full: armed by the leader's producer with the byte count of BOTH CTAs' loads; tempty: every epilogue warp of the pair
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS * CG); }
     fence_mbar_init();
   }
-  if (warp == W_MMA) tmem_alloc<TMEM_COLS>(base + OFF_BAR + NUM_BARS * 8);
+  if (warp == W_MMA) {
+    if (CG == 2) tmem_alloc_2cta<TMEM_COLS>(base + OFF_BAR + NUM_BARS * 8);
+    else tmem_alloc<TMEM_COLS>(base + OFF_BAR + NUM_BARS * 8);
+  }
   tcgen05_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
   int M_eff = p.M;
   if (p.m_dev != nullptr) { int m = *p.m_dev; M_eff = m < p.M ? (m < 0 ? 0 : m) : p.M; }
-  const int tiles_m = (M_eff + BM - 1) / BM;
+  constexpr int TILE_M = BM * CG;
+  const int tiles_m = (M_eff + TILE_M - 1) / TILE_M;
   const int tiles_n = (p.N + BN - 1) / BN;
   const int num_tiles = tiles_m * tiles_n;
   const int k_blocks = (p.K + BK - 1) / BK;
+  const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;   // both CTAs of a pair walk the same tiles
 
   if (warp == W_TMA) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int t = tile0; t < num_tiles; t += tile_step) {
         const int m_blk = t / tiles_n, n_blk = t % tiles_n;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
-          tma_load_2d(&tmA, full_bar(stage), base + OFF_A + stage * A_STAGE_BYTES, kb * BK, m_blk * BM);
-          tma_load_2d(&tmB, full_bar(stage), base + OFF_B + stage * B_STAGE_BYTES, kb * BK, n_blk * BN);
+          if (CG == 2) {
+            // both CTAs' bytes are counted on the LEADER's full barrier (the MMA issuer waits there).  The peer cannot
+            // run a phase ahead: its empty barrier for this stage fires only after the MMAs that consumed the stage
+            // retired, i.e. after the leader's full barrier already flipped.
+            const uint32_t lead_full = mapa_shared(full_bar(stage), 0);
+            if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
+            tma_load_2d_2sm(&tmA, lead_full, base + OFF_A + stage * A_STAGE_BYTES, kb * BK, m_blk * TILE_M + static_cast<int>(rank) * BM);
+            tma_load_2d_2sm(&tmB, lead_full, base + OFF_B + stage * B_STAGE_BYTES, kb * BK, n_blk * BN + static_cast<int>(rank) * (BN / 2));
+          } else {
+            mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+            tma_load_2d(&tmA, full_bar(stage), base + OFF_A + stage * A_STAGE_BYTES, kb * BK, m_blk * BM);
+            tma_load_2d(&tmB, full_bar(stage), base + OFF_B + stage * B_STAGE_BYTES, kb * BK, n_blk * BN);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == W_MMA) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int t = tile0; t < num_tiles; t += tile_step) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
@@ -119,12 +147,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t adesc = umma_desc_k_sw128(a_addr + k * UMMA_K * 2);
             const uint64_t bdesc = umma_desc_k_sw128(b_addr + k * UMMA_K * 2);
-            umma_f16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (CG == 2) umma_f16_2cta(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_f16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));          // smem slot reusable once these MMAs retire
+          // smem slot reusable once these MMAs retire (in both CTAs of a pair)
+          if (CG == 2) umma_commit_2cta_mc(empty_bar(stage), 3); else umma_commit(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));              // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if (CG == 2) umma_commit_2cta_mc(tfull_bar(acc), 3); else umma_commit(tfull_bar(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -140,9 +171,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int j = lane & 7;                       // 16-byte column chunk handled in the coalesced phase
     const int rsub = lane >> 3;                   // row (mod 4) handled in the coalesced phase
     const float* bias = p.bias;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int t = tile0; t < num_tiles; t += tile_step) {
       const int m_blk = t / tiles_n, n_blk = t % tiles_n;
-      const int row0 = m_blk * BM + q * 32;
+      const int row0 = m_blk * TILE_M + static_cast<int>(rank) * BM + q * 32;
       const int n0 = n_blk * BN + half * 128;
       bool waited = false;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + half * 128);
@@ -244,16 +275,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       if (!waited) { mbar_wait(tfull_bar(acc), acc_phase); tcgen05_fence_after(); }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));   // the leader's MMA issuer waits on it
+        else mbar_arrive(tempty_bar(acc));
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();   // pair: nobody leaves while the peer may still touch its smem/TMEM
   if (warp == W_MMA) {
     tcgen05_fence_after();
-    tmem_dealloc<TMEM_COLS>(tmem_base);
+    if (CG == 2) tmem_dealloc_2cta<TMEM_COLS>(tmem_base); else tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 
@@ -292,6 +326,8 @@ int make_tmap_2d_bf16(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t 
 
 }  // namespace
 
+int g_gemm_cta_group = 0;   // 0 = automatic; 1 forces single-CTA tiles (debug / A-B timing via setok_debug_set_gemm_cta_group)
+
 int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   SETOK_REQUIRE(g.A && g.W && g.D, SETOK_ERR_BAD_ARG, "gemm: null operand");
   SETOK_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, SETOK_ERR_BAD_ARG, "gemm: non-positive shape M=%d N=%d K=%d", g.M, g.N, g.K);
@@ -312,37 +348,53 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   const int res_kind = g.residual ? (g.residual_dtype == SETOK_BF16 ? 1 : 2) : 0;
   const int out_f32 = g.out_dtype == SETOK_F32 ? 1 : 0;
   // specialised epilogues for the combinations the tokenizer path launches; everything else -> generic
-  KernelFn fn = gemm_bf16_tcgen05_kernel<-1, -1, -1, -1>;
+  // CTA pairs whenever there is at least one full 256-row tile; single CTAs for short row counts
+  const int cg = (g.M >= 256 && g_gemm_cta_group != 1) ? 2 : 1;
+#define SETOK_PICK(A, R, O, P) (cg == 2 ? gemm_bf16_tcgen05_kernel<2, A, R, O, P> : gemm_bf16_tcgen05_kernel<1, A, R, O, P>)
+  KernelFn fn = SETOK_PICK(-1, -1, -1, -1);
   if (g.remap_P == 0) {
-    if (g.act == SETOK_ACT_NONE && res_kind == 0 && !out_f32) fn = gemm_bf16_tcgen05_kernel<0, 0, 0, 0>;              // qkv
-    else if (g.act == SETOK_ACT_NONE && res_kind == 1 && !out_f32) fn = gemm_bf16_tcgen05_kernel<0, 1, 0, 0>;         // ViT out_proj / fc2
-    else if (g.act == SETOK_ACT_QUICK_GELU && res_kind == 0 && !out_f32) fn = gemm_bf16_tcgen05_kernel<1, 0, 0, 0>;   // ViT fc1
-    else if (g.act == SETOK_ACT_GELU_ERF && res_kind == 0 && !out_f32) fn = gemm_bf16_tcgen05_kernel<2, 0, 0, 0>;     // head / projector fc1
-    else if (g.act == SETOK_ACT_NONE && res_kind == 2 && out_f32) fn = gemm_bf16_tcgen05_kernel<0, 2, 1, 0>;          // head proj / fc2
-    else if (g.act == SETOK_ACT_NONE && res_kind == 0 && out_f32) fn = gemm_bf16_tcgen05_kernel<0, 0, 1, 0>;          // out / projector last
+    if (g.act == SETOK_ACT_NONE && res_kind == 0 && !out_f32) fn = SETOK_PICK(0, 0, 0, 0);              // qkv
+    else if (g.act == SETOK_ACT_NONE && res_kind == 1 && !out_f32) fn = SETOK_PICK(0, 1, 0, 0);         // ViT out_proj / fc2
+    else if (g.act == SETOK_ACT_QUICK_GELU && res_kind == 0 && !out_f32) fn = SETOK_PICK(1, 0, 0, 0);   // ViT fc1
+    else if (g.act == SETOK_ACT_GELU_ERF && res_kind == 0 && !out_f32) fn = SETOK_PICK(2, 0, 0, 0);     // head / projector fc1
+    else if (g.act == SETOK_ACT_NONE && res_kind == 2 && out_f32) fn = SETOK_PICK(0, 2, 1, 0);          // head proj / fc2
+    else if (g.act == SETOK_ACT_NONE && res_kind == 0 && out_f32) fn = SETOK_PICK(0, 0, 1, 0);          // out / projector last
   } else if (g.act == SETOK_ACT_NONE && res_kind == 2 && out_f32) {
-    fn = gemm_bf16_tcgen05_kernel<0, 2, 1, 1>;                                                                         // patch embedding
+    fn = SETOK_PICK(0, 2, 1, 1);                                                                         // patch embedding
   }
+#undef SETOK_PICK
+  const int smem_bytes = cg == 2 ? Cfg<2>::SMEM_BYTES : Cfg<1>::SMEM_BYTES;
   static std::mutex attr_mu;
   static std::set<KernelFn> attr_done;
   {
     std::lock_guard<std::mutex> lk(attr_mu);
     if (!attr_done.count(fn)) {
-      SETOK_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      SETOK_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
       attr_done.insert(fn);
     }
   }
   CUtensorMap tmA, tmB;
   SETOK_TRY(make_tmap_2d_bf16(&tmA, g.A, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)g.lda, BM));
-  SETOK_TRY(make_tmap_2d_bf16(&tmB, g.W, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldw, BN));
+  SETOK_TRY(make_tmap_2d_bf16(&tmB, g.W, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldw, BN / cg));
   GemmDev p;
   p.D = g.D; p.ldd = g.ldd; p.bias = g.bias; p.res = g.residual; p.ldr = g.ldr; p.m_dev = g.m_dev;
   p.M = g.M; p.N = g.N; p.K = g.K; p.act = g.act; p.out_f32 = g.out_dtype == SETOK_F32;
   p.res_kind = res_kind;
   p.remap_P = g.remap_P;
-  const int tiles = ceil_div(g.M, BM) * ceil_div(g.N, BN);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  fn<<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
+  const int tiles = ceil_div(g.M, BM * cg) * ceil_div(g.N, BN);
+  const int max_groups = num_sms() / cg;
+  const int grid = (tiles < max_groups ? tiles : max_groups) * cg;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cg; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SETOK_CUDA_OK(cudaLaunchKernelEx(&cfg, fn, tmA, tmB, p));
   SETOK_LAUNCH_CHECK();
   return SETOK_OK;
 }
@@ -355,3 +407,5 @@ extern "C" int setok_gemm_bf16(const void* A, int64_t lda, const void* W, int64_
   setok::GemmArgs g{A, lda, W, ldw, D, ldd, out_dtype, bias, residual, ldr, residual_dtype, act, M, N, K, m_dev, 0};
   return setok::launch_gemm(g, static_cast<cudaStream_t>(stream));
 }
+
+extern "C" void setok_debug_set_gemm_cta_group(int cg) { setok::g_gemm_cta_group = cg; }

@@ -32,6 +32,13 @@ def main():
     x = torch.randn(M, C, device=dev, generator=g).to(torch.bfloat16)
     shapes = {"qkv": (a, 3 * C, C, ops.ACT_NONE, False), "out_proj": (a, C, C, ops.ACT_NONE, True),
               "fc1": (a, F, C, ops.ACT_QUICK_GELU, False), "fc2": (u, C, F, ops.ACT_NONE, True)}
+    import ctypes
+    from setok_b200 import _lib
+    lib = _lib.load()
+    cg = int(os.environ.get("SETOK_GEMM_CG", "0"))
+    lib.setok_debug_set_gemm_cta_group.argtypes = [ctypes.c_int]
+    lib.setok_debug_set_gemm_cta_group(cg)
+    print(f"gemm cta_group setting: {cg} (0 = auto: pairs when M >= 256)")
     tot_ms = tot_fl = 0
     for name, (inp, n, k, act, res) in shapes.items():
         w = (torch.randn(n, k, device=dev, generator=g) * k ** -0.5).to(torch.bfloat16)
