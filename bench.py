@@ -295,24 +295,21 @@ def run_ours(args):
     host_noise = noise.cpu().pin_memory()
     h2d = host_images.numel() * 4 + host_noise.numel() * 4
 
-    def e2e_step():
-        d_img = host_images.to(dev, non_blocking=True)
-        d_noise = host_noise.to(dev, non_blocking=True)
-        r, i, s = tok(d_img, k=KNN_K, noise=d_noise)
-        if gather:
-            r = all_gather_ragged(r)
-        toks = r.packed().cpu()                     # syncs on offsets, then copies the live rows
-        offs = r.offsets.cpu()
-        i_h, s_h = i.cpu(), s.cpu()
-        return toks.numel() * toks.element_size() + offs.numel() * 4 + i_h.numel() * 8 + s_h.numel() * 4
+    from setok_b200.pipeline import stream_tokenize
 
-    for _ in range(3):
-        d2h = e2e_step()
+    def e2e_run(n_steps):
+        """n_steps batches through the public streaming API: each step copies its images+noise in from pinned host memory
+        and its ragged result (tokens, offsets, labels, scores) back out."""
+        post = (lambda r, i, s_: (all_gather_ragged(r), i, s_)) if gather else None
+        nbytes = 0
+        for res in stream_tokenize(tok, ((host_images, host_noise) for _ in range(n_steps)), post=post, k=KNN_K):
+            nbytes = res.nbytes
+        return nbytes
+
+    d2h = e2e_run(3)
     barrier()
-    t0 = time.perf_counter()
     e0.record()
-    for _ in range(args.steps):
-        d2h = e2e_step()
+    d2h = e2e_run(args.steps)
     e1.record()
     barrier()
     ms_e = e0.elapsed_time(e1)

@@ -94,7 +94,10 @@ attn_tcgen05_hd64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_co
       }
     }
   } else if (warp == W_MMA) {
-    if (lane == 0) {
+    {
+      // The whole warp runs this role convergently (waits included) and one elected lane issues the tcgen05
+      // instructions: with warp-uniform control flow the descriptors live in uniform registers, which the MMA needs,
+      // instead of being moved there lane-by-lane before every instruction (this issue path is on the critical chain).
       // all operand descriptors are loop-invariant: build them once
       // (stage s of K/V only shifts the 14-bit address field by s * KV_STAGE / 16)
       const uint64_t dq0 = umma_desc_k_sw128(base + OFF_Q), dq1 = dq0 + 2, dq2 = dq0 + 4, dq3 = dq0 + 6;   // +32 B per k-step
@@ -112,31 +115,37 @@ attn_tcgen05_hd64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_co
         mbar_wait(kv_full(st_), (j_ / KV_STAGES) & 1);                                                 \
         tcgen05_fence_after();                                                                         \
         const uint64_t soff_ = static_cast<uint64_t>(st_ * (KV_STAGE >> 4));                           \
-        umma_f16(tmem_base, dq0, dk0 + soff_, idesc_, 0u);                                             \
-        umma_f16(tmem_base, dq1, dk1 + soff_, idesc_, 1u);                                             \
-        umma_f16(tmem_base, dq2, dk2 + soff_, idesc_, 1u);                                             \
-        umma_f16(tmem_base, dq3, dk3 + soff_, idesc_, 1u);                                             \
-        umma_commit(s_full);                                                                           \
+        if (elect_one_sync()) {                                                                        \
+          umma_f16(tmem_base, dq0, dk0 + soff_, idesc_, 0u);                                           \
+          umma_f16(tmem_base, dq1, dk1 + soff_, idesc_, 1u);                                           \
+          umma_f16(tmem_base, dq2, dk2 + soff_, idesc_, 1u);                                           \
+          umma_f16(tmem_base, dq3, dk3 + soff_, idesc_, 1u);                                           \
+          umma_commit(s_full);                                                                         \
+        }                                                                                              \
+        __syncwarp();                                                                                  \
       } while (0)
       mbar_wait(q_full, 0);
-      TRACE(2);
+      if (lane == 0) TRACE(2);
       ISSUE_S(0);
-      TRACE(3);
+      if (lane == 0) TRACE(3);
       for (int j = 0; j < nchunks; ++j) {
         const int nk16 = min(KT, ((T - j * KT) + 15) & ~15) >> 4;
         mbar_wait(p_full, j & 1);
-        TRACE(10 + 4 * j);
+        if (lane == 0) TRACE(10 + 4 * j);
         tcgen05_fence_after();
         const int st = j % KV_STAGES;
         const uint64_t soff = static_cast<uint64_t>(st * (KV_STAGE >> 4));
-        umma_f16(tmem_base + O_COL, dp0, dv0 + soff, idesc_pv, j != 0 ? 1u : 0u);
-        if (nk16 > 1) umma_f16(tmem_base + O_COL, dp1, dv1 + soff, idesc_pv, 1u);
-        if (nk16 > 2) umma_f16(tmem_base + O_COL, dp2, dv2 + soff, idesc_pv, 1u);
-        if (nk16 > 3) umma_f16(tmem_base + O_COL, dp3, dv3 + soff, idesc_pv, 1u);
-        umma_commit(kv_empty(st));
+        if (elect_one_sync()) {
+          umma_f16(tmem_base + O_COL, dp0, dv0 + soff, idesc_pv, j != 0 ? 1u : 0u);
+          if (nk16 > 1) umma_f16(tmem_base + O_COL, dp1, dv1 + soff, idesc_pv, 1u);
+          if (nk16 > 2) umma_f16(tmem_base + O_COL, dp2, dv2 + soff, idesc_pv, 1u);
+          if (nk16 > 3) umma_f16(tmem_base + O_COL, dp3, dv3 + soff, idesc_pv, 1u);
+          umma_commit(kv_empty(st));
+          if (j + 1 >= nchunks) umma_commit(o_final);
+        }
+        __syncwarp();
         if (j + 1 < nchunks) ISSUE_S(j + 1);
-        else umma_commit(o_final);
-        TRACE(11 + 4 * j);
+        if (lane == 0) TRACE(11 + 4 * j);
       }
     }
   } else {

@@ -181,6 +181,14 @@ __device__ __forceinline__ void tma_load_3d(const void* tmap, uint32_t bar, uint
       : "memory");
 }
 
+// One lane of a fully converged warp (warp-uniform code keeps descriptor arithmetic in the uniform datapath;
+// only the tcgen05 instruction itself is predicated on the elected lane).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- tcgen05 / TMEM ---------------------------------------------------------------------------
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
