@@ -199,9 +199,22 @@ def quick_gelu(x: torch.Tensor) -> torch.Tensor:
     return x * torch.sigmoid(1.702 * x)
 
 
+def interpolated_pos_embedding(pos: torch.Tensor, new_grid: int) -> torch.Tensor:
+    """CLIPVisionEmbeddings.interpolate_pos_encoding (modeling_clip.py:160-196): class row kept, the patch grid resized
+    with bicubic interpolation (align_corners=False).  pos (1+g*g, C) -> (1+new_grid^2, C)."""
+    n = pos.shape[0] - 1
+    g = int(n ** 0.5)
+    if g == new_grid:
+        return pos
+    C = pos.shape[1]
+    grid = pos[1:].reshape(1, g, g, C).permute(0, 3, 1, 2)
+    grid = F.interpolate(grid, size=(new_grid, new_grid), mode="bicubic", align_corners=False)
+    return torch.cat([pos[:1], grid.permute(0, 2, 3, 1).reshape(-1, C)], dim=0)
+
+
 def clip_vit_hidden_states(images: torch.Tensor, p: Params, *, patch: int, heads: int, layers: int,
                            prefix: str = "vision_model.", n_layers_run: Optional[int] = None,
-                           eps: float = 1e-5) -> List[torch.Tensor]:
+                           eps: float = 1e-5, interpolate_pos_encoding: bool = False) -> List[torch.Tensor]:
     """Returns HF's `hidden_states` tuple: [pre_layrnorm(embeddings), layer_1 out, ..., layer_L out].
     `n_layers_run` stops early (only hidden_states[:n+1] are produced)."""
     B = images.shape[0]
@@ -209,7 +222,12 @@ def clip_vit_hidden_states(images: torch.Tensor, p: Params, *, patch: int, heads
     C = Wp.shape[0]
     pe = F.conv2d(images.to(Wp.dtype), Wp, None, stride=patch).flatten(2).transpose(1, 2)   # (B, N, C)
     cls = p[prefix + "embeddings.class_embedding"].expand(B, 1, C)
-    x = torch.cat([cls, pe], dim=1) + p[prefix + "embeddings.position_embedding.weight"][None]
+    pos = p[prefix + "embeddings.position_embedding.weight"]
+    if pos.shape[0] != pe.shape[1] + 1:
+        if not interpolate_pos_encoding:
+            raise ValueError(f"Input image size ({images.shape[2]}*{images.shape[3]}) doesn't match model.")
+        pos = interpolated_pos_embedding(pos, images.shape[2] // patch)
+    x = torch.cat([cls, pe], dim=1) + pos[None]
     x = F.layer_norm(x, (C,), p[prefix + "pre_layrnorm.weight"], p[prefix + "pre_layrnorm.bias"], eps)
     hs = [x]
     hd = C // heads
@@ -242,13 +260,14 @@ def layers_needed(select_layer: int, layers: int) -> int:
 
 def tower_features(images: torch.Tensor, p: Params, *, patch: int, heads: int, layers: int,
                    select_layer: int = -2, select_feature: str = "patch",
-                   prefix: str = "vision_model.") -> torch.Tensor:
+                   prefix: str = "vision_model.", interpolate_pos_encoding: bool = False) -> torch.Tensor:
     """clip_encoder.py:50-62 + feature_select :40-48: hidden_states[select_layer], CLS dropped for
     'patch', kept for 'cls_patch', anything else raises ValueError (:47)."""
     if select_feature not in ("patch", "cls_patch"):
         raise ValueError(f"Unexpected select feature: {select_feature}")
     n = layers_needed(select_layer, layers)
-    hs = clip_vit_hidden_states(images, p, patch=patch, heads=heads, layers=layers, prefix=prefix, n_layers_run=n)
+    hs = clip_vit_hidden_states(images, p, patch=patch, heads=heads, layers=layers, prefix=prefix, n_layers_run=n,
+                                interpolate_pos_encoding=interpolate_pos_encoding)
     f = hs[n]
     if select_feature == "patch":
         f = f[:, 1:]

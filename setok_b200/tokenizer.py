@@ -224,7 +224,32 @@ class CLIPVisionTower(nn.Module):
                        cls=keep["cls"].data_ptr(), pos=keep["pos"].data_ptr(), pre_ln_g=keep["pre_g"].data_ptr(),
                        pre_ln_b=keep["pre_b"].data_ptr(), layer=layers)
         self._packed = (vit, layers, keep)
+        self._resized = {}
         return self._packed
+
+    def _vit_for_size(self, size: int):
+        """The packed tower for `size`^2 inputs.  Other than the native size needs `interpolate_pos_encoding`: the position
+        table is resized once per size exactly as HF does (bicubic on the patch grid, class row kept;
+        modeling_clip.py:160-196) and cached; all kernels take the grid size as a run-time argument."""
+        vit, layers, keep = self._packed or self._pack()
+        if size == vit.image_size:
+            return vit
+        hit = self._resized.get(size)
+        if hit is None:
+            if size % vit.patch != 0:
+                raise SetokError(f"image size {size} is not a multiple of the patch size {vit.patch}")
+            pos = keep["pos"].detach().float().cpu()
+            g = int((pos.shape[0] - 1) ** 0.5)
+            ng = size // vit.patch
+            grid = pos[1:].reshape(1, g, g, -1).permute(0, 3, 1, 2)
+            grid = torch.nn.functional.interpolate(grid, size=(ng, ng), mode="bicubic", align_corners=False)
+            new_pos = torch.cat([pos[:1], grid.permute(0, 2, 3, 1).reshape(ng * ng, -1)], 0).contiguous().to(keep["pos"].device)
+            v2 = _lib.Vit(image_size=size, patch=vit.patch, hidden=vit.hidden, heads=vit.heads, layers=vit.layers, mlp=vit.mlp,
+                          ln_eps=vit.ln_eps, w_patch=vit.w_patch, cls=vit.cls, pos=new_pos.data_ptr(), pre_ln_g=vit.pre_ln_g,
+                          pre_ln_b=vit.pre_ln_b, layer=layers)
+            hit = (v2, new_pos)
+            self._resized[size] = hit
+        return hit[0]
 
     def layers_to_run(self) -> int:
         L = self.config.num_hidden_layers
@@ -234,11 +259,11 @@ class CLIPVisionTower(nn.Module):
         return idx
 
     @torch.no_grad()
-    def forward(self, images):
+    def forward(self, images, interpolate_pos_encoding: bool = False):
         if self.select_feature not in ("patch", "cls_patch"):
             raise ValueError(f"Unexpected select feature: {self.select_feature}")
         if type(images) is list:       # clip_encoder.py:52-57: per-image loop -> list of (1, N, C)
-            return [self.forward(im.unsqueeze(0)) for im in images]
+            return [self.forward(im.unsqueeze(0), interpolate_pos_encoding) for im in images]
         if not self.is_loaded:
             raise SetokError("vision tower not loaded: call load_model() first")
         vit, _, _ = self._packed or self._pack()
@@ -246,8 +271,10 @@ class CLIPVisionTower(nn.Module):
         if images.dim() != 4 or images.shape[1] != 3:
             raise SetokError(f"images must be (B, 3, H, W); got {tuple(images.shape)}")
         if images.shape[2] != vit.image_size or images.shape[3] != vit.image_size:
-            raise ValueError(f"Input image size ({images.shape[2]}*{images.shape[3]}) doesn't match model "
-                             f"({vit.image_size}*{vit.image_size}).")
+            if not interpolate_pos_encoding or images.shape[2] != images.shape[3]:      # HF raises likewise (modeling_clip.py:204-207)
+                raise ValueError(f"Input image size ({images.shape[2]}*{images.shape[3]}) doesn't match model "
+                                 f"({vit.image_size}*{vit.image_size}).")
+            vit = self._vit_for_size(int(images.shape[2]))
         out_dtype = images.dtype
         x = images.to(device=dev)
         if x.dtype not in (torch.float32, torch.bfloat16):
@@ -460,12 +487,38 @@ class SetokTokenizer(nn.Module):
         return rt, idx, score.unsqueeze(1)
 
     @torch.no_grad()
-    def forward(self, x, k=None, threshold=None, token_mask=None, noise: Optional[torch.Tensor] = None):
+    def forward(self, x, k=None, threshold=None, token_mask=None, noise=None, interpolate_pos_encoding: bool = False):
         """x: images (B, 3, H, W) (or a list of (3, H, W)).  Returns the reference's 3-tuple
         ``(group_features, idx_cluster, score)`` (tokenizer.py:182) for the whole batch: ``group_features`` is a
         RaggedTokens whose ``[b]`` is image b's (K_b, C_tok) tensor, ``idx_cluster`` is (B, N) int64 and
-        ``score[b]`` has the reference's (1, N) shape."""
-        feats = self.image_feature_encoder(x)
-        if isinstance(feats, list):
-            feats = torch.cat(feats, dim=0)
+        ``score[b]`` has the reference's (1, N) shape.
+
+        A list whose images differ in resolution (BASELINE config 5; needs ``interpolate_pos_encoding=True``) is
+        processed as one batch per resolution and re-packed in the original image order; ``idx_cluster`` / ``score``
+        are then per-image lists because N differs, and ``noise`` is a list of (N_i,) tensors."""
+        if isinstance(x, (list, tuple)) and len({tuple(im.shape) for im in x}) > 1:
+            return self._forward_mixed(list(x), k, threshold, noise, interpolate_pos_encoding)
+        if isinstance(x, (list, tuple)):
+            x = torch.stack(list(x), dim=0)
+            if isinstance(noise, (list, tuple)):
+                noise = torch.stack(list(noise), dim=0)
+        feats = self.image_feature_encoder(x, interpolate_pos_encoding)
         return self.encode_features(feats, k=k, threshold=threshold, token_mask=token_mask, noise=noise)
+
+    def _forward_mixed(self, images, k, threshold, noise, interpolate_pos_encoding):
+        groups: Dict[tuple, List[int]] = {}
+        for i, im in enumerate(images):
+            groups.setdefault(tuple(im.shape), []).append(i)
+        B = len(images)
+        per_tokens: List[Optional[torch.Tensor]] = [None] * B
+        idxs: List[Optional[torch.Tensor]] = [None] * B
+        scores: List[Optional[torch.Tensor]] = [None] * B
+        for shape, members in groups.items():
+            batch = torch.stack([images[i] for i in members], dim=0)
+            nz = None if noise is None else torch.stack([noise[i] for i in members], dim=0)
+            rt, idx, score = self.forward(batch, k=k, threshold=threshold, noise=nz, interpolate_pos_encoding=interpolate_pos_encoding)
+            for j, i in enumerate(members):
+                per_tokens[i], idxs[i], scores[i] = rt[j], idx[j], score[j]
+        counts = torch.tensor([0] + [t.shape[0] for t in per_tokens], dtype=torch.int32)
+        offsets = torch.cumsum(counts, 0).to(dtype=torch.int32, device=self.device)
+        return RaggedTokens(torch.cat(per_tokens, dim=0), offsets), idxs, scores

@@ -226,3 +226,102 @@ def test_builder_and_state_dict_surface():
     tok.invalidate()
     rt2, _, _ = tok(torch.randn(3, 3, 16, 16, device=DEV, generator=torch.Generator(device=DEV).manual_seed(0)))
     assert rt2.data.shape[1] == 64
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE.json configurations as parity cases (configs[1] is the bench workload; the others run here)
+# ---------------------------------------------------------------------------------------------------
+def test_config1_vit_b16_fixed_k32_single_image():
+    """configs[0]: single 224^2 image, ViT-B/16 (12 layers, C=768, N=196), threshold 1e9 forces the top-k fallback:
+    K == min_cluster_num == 32 exactly, centres ascending (tokenizer.py:104-107)."""
+    C, L, H, P, IMG = 768, 12, 12, 16, 224
+    cfg = dict(hidden_size=C, intermediate_size=4 * C, num_hidden_layers=L, num_attention_heads=H, image_size=IMG, patch_size=P)
+    tp = O.make_tower_params(C, L, H, P, IMG, seed=21)
+    hp = O.make_head_params(C, C, 4096, seed=22)
+    tok = _make_tokenizer(C, C, 4096, 32, 1e9, cfg, select_layer=-2, tower_sd=tp, head_sd=hp)
+    img = torch.randn(1, 3, IMG, IMG, generator=torch.Generator().manual_seed(23))
+    noise = O.tie_noise(196, 24)[None]
+    rt, idx, score = tok(img.to(DEV), k=32, noise=noise.to(DEV))
+    assert rt.counts == [32] and rt[0].shape == (32, C) and idx.shape == (1, 196) and score.shape == (1, 1, 196)
+    down = rt.index_down[0, :32].cpu()
+    assert torch.equal(torch.sort(down).values, down) and int(idx.max()) == 31
+    feats = tok.image_feature_encoder(img.to(DEV)).cpu()
+    ref = O.tower_features(img, tp, patch=P, heads=H, layers=L, select_layer=-2)
+    assert _err(feats, ref)[1] < 1e-2
+    toks, oidx, oscore, im = O.tokenizer_head(feats[0], noise[0], hp, min_cluster_num=32, threshold=1e9, k=32, return_intermediates=True)
+    m = O.dpc_margins(im["x"], 32, noise[0], 1e9, 32)
+    if m["threshold_margin"] > 2e-4:
+        assert torch.equal(down, im["index_down"])
+        firm = m["token_gap"] > 2e-4
+        assert torch.equal(idx[0].cpu()[firm], oidx[firm])
+        if bool(firm.all()):
+            assert _err(rt[0], toks)[1] < 1e-2
+
+
+def test_config3_tokenizer_at_336_bf16():
+    """configs[2], tokenizer half: 336^2 -> N = 576 patches (T = 577: five 128-row attention tiles, ten K/V chunks), bf16 in/out."""
+    C, L, H, P, IMG, B = 1024, 2, 16, 14, 336, 2
+    cfg = dict(hidden_size=C, intermediate_size=4 * C, num_hidden_layers=L, num_attention_heads=H, image_size=IMG, patch_size=P)
+    tp = O.make_tower_params(C, L, H, P, IMG, seed=31)
+    hp = O.make_head_params(C, C, 4096, seed=32)
+    tok = _make_tokenizer(C, C, 4096, 64, 0.5, cfg, select_layer=-1, tower_sd=tp, head_sd=hp)
+    imgs = torch.randn(B, 3, IMG, IMG, generator=torch.Generator().manual_seed(33))
+    ref = O.tower_features(imgs, tp, patch=P, heads=H, layers=L, select_layer=-1)
+    got = tok.image_feature_encoder(imgs.to(DEV, torch.bfloat16))
+    assert got.dtype == torch.bfloat16 and got.shape == (B, 576, C)
+    assert _err(got, ref)[1] < 1.5e-2
+    rt, idx, score = tok(imgs.to(DEV, torch.bfloat16), k=16)
+    assert rt.dtype == torch.bfloat16 and idx.shape == (B, 576) and all(1 <= c <= 576 for c in rt.counts)
+
+
+def test_config4_encode_images_to_vicuna_projector_bf16():
+    """configs[3], one rank's share: encode_images -> mlp2x_gelu projector C_tok -> 4096 -> 4096 (Vicuna-7B width), bf16,
+    against the oracle projector applied to the tokenizer's own tokens."""
+    C, L, H, P, IMG, B = 1024, 1, 16, 14, 224, 4
+    cfg = dict(hidden_size=C, intermediate_size=4 * C, num_hidden_layers=L, num_attention_heads=H, image_size=IMG, patch_size=P)
+    tok = _make_tokenizer(C, C, 4096, 64, 0.5, cfg, select_layer=-1, tower_sd=O.make_tower_params(C, L, H, P, IMG, seed=41),
+                          head_sd=O.make_head_params(C, C, 4096, seed=42))
+    pp = O.make_projector_params(C, 4096, "mlp2x_gelu", seed=43)
+    proj = build_vision_projector("mlp2x_gelu", mm_hidden_size=C, hidden_size=4096)
+    proj.load_state_dict(pp)
+    proj = proj.to(DEV)
+    imgs = torch.randn(B, 3, IMG, IMG, generator=torch.Generator().manual_seed(44)).to(DEV, torch.bfloat16)
+    noise = torch.rand(B, 256, generator=torch.Generator().manual_seed(45)).to(DEV)
+    rt, _, _ = tok(imgs, k=16, noise=noise)
+    out = encode_images(tok, proj, imgs, k=16, noise=noise)
+    assert out.batch_size == B and out.data.shape[1] == 4096 and out.dtype == torch.bfloat16 and out.counts == rt.counts
+    for b in range(B):
+        ref = O.projector(rt[b].float().cpu(), pp, "mlp2x_gelu")
+        mx, fro = _err(out[b], ref)
+        assert fro < 1.5e-2, (b, mx, fro)
+
+
+def test_config5_mixed_resolution_ragged_batch():
+    """configs[4]: one batch mixing 224^2 / 336^2 / 448^2 images (N = 256 / 576 / 1024) through a tower whose position
+    table is bicubically resized per resolution (HF interpolate_pos_encoding), re-packed in image order."""
+    C, L, H, P, IMG = 1024, 1, 16, 14, 224
+    cfg = dict(hidden_size=C, intermediate_size=4 * C, num_hidden_layers=L, num_attention_heads=H, image_size=IMG, patch_size=P)
+    tp = O.make_tower_params(C, L, H, P, IMG, seed=51)
+    hp = O.make_head_params(C, C, 4096, seed=52)
+    tok = _make_tokenizer(C, C, 4096, 64, 0.5, cfg, select_layer=-1, tower_sd=tp, head_sd=hp)
+    g = torch.Generator().manual_seed(53)
+    sizes = [224, 448, 336, 224, 336]
+    images = [torch.randn(3, s, s, generator=g) for s in sizes]
+    noise = [O.tie_noise((s // P) ** 2, 60 + i) for i, s in enumerate(sizes)]
+    with pytest.raises(ValueError):
+        tok([im.to(DEV) for im in images], k=16)                     # HF raises without the flag
+    rt, idxs, scores = tok([im.to(DEV) for im in images], k=16, noise=[n.to(DEV) for n in noise], interpolate_pos_encoding=True)
+    assert rt.batch_size == 5 and [i.shape[0] for i in idxs] == [(s // P) ** 2 for s in sizes]
+    assert rt.total == sum(rt.counts) and scores[1].shape == (1, 1024)
+    for i, s in enumerate(sizes):
+        ref = O.tower_features(images[i][None], tp, patch=P, heads=H, layers=L, select_layer=-1, interpolate_pos_encoding=True)
+        feats = tok.image_feature_encoder(images[i][None].to(DEV), True).cpu()
+        assert feats.shape == ref.shape and _err(feats, ref)[1] < 1e-2, (i, s)
+        toks, oidx, oscore, im = O.tokenizer_head(feats[0], noise[i], hp, min_cluster_num=64, threshold=0.5, k=16, return_intermediates=True)
+        m = O.dpc_margins(im["x"], 16, noise[i], 0.5, 64)
+        if m["threshold_margin"] > 2e-4:
+            firm = m["token_gap"] > 2e-4
+            assert rt[i].shape == toks.shape
+            assert torch.equal(idxs[i].cpu()[firm], oidx[firm]), (i, s)
+            if bool(firm.all()):
+                assert _err(rt[i], toks)[1] < 1e-2

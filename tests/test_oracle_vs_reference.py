@@ -71,3 +71,19 @@ def test_tower_live_vit_b16_shape(ns):
         ref = tok.image_feature_encoder(img)
     f = O.tower_features(img, dict(hf.state_dict()), patch=16, heads=3, layers=3, select_layer=-2)
     torch.testing.assert_close(f, ref, rtol=1e-4, atol=1e-5)
+
+
+def test_interpolated_pos_encoding_live(ns):
+    """Oracle's bicubic position-table resize vs HF's `interpolate_pos_encoding=True` (BASELINE config 5)."""
+    from transformers import CLIPVisionConfig, CLIPVisionModel
+    torch.manual_seed(0)
+    cfg = CLIPVisionConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=2, image_size=32, patch_size=8)
+    cfg._attn_implementation = "eager"
+    hf = CLIPVisionModel(cfg).eval()
+    img = torch.randn(2, 3, 48, 48)
+    with torch.no_grad():
+        ref = hf(img, output_hidden_states=True, interpolate_pos_encoding=True).hidden_states[-1][:, 1:]
+    f = O.tower_features(img, dict(hf.state_dict()), patch=8, heads=2, layers=2, select_layer=-1, interpolate_pos_encoding=True)
+    torch.testing.assert_close(f, ref, rtol=1e-4, atol=1e-5)
+    with pytest.raises(ValueError):
+        O.tower_features(img, dict(hf.state_dict()), patch=8, heads=2, layers=2, select_layer=-1)
