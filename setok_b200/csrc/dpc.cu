@@ -4,7 +4,7 @@
 // Three launches per batch:
 //   1. posadd_sqnorm_kernel   x_pos = feats + pos (fp32), row squared norms           (HBM-bound)
 //   2. gram_dist_kernel       D[b] = sqrt(max(n_i + n_j - 2 x_i.x_j, 0)) / sqrt(C)     (fp32 FMA; the
-//                             matmul form torch.cdist takes for N > 25)
+//                             matmul form torch.cdist takes for N > 25); upper-triangular tiles only, mirrored
 //   3. dpc_select_kernel      one CTA per image on D[b] (L2-resident): kNN density by bitwise
 //                             selection, the column-indexed row-max fill of tokenizer.py:98-99,
 //                             score, threshold / top-k fallback, ordered compaction, argmin assignment.
@@ -61,6 +61,9 @@ __global__ void __launch_bounds__(256) gram_dist_kernel(const float* __restrict_
   __shared__ __align__(16) float As[GK][GT + 4];
   __shared__ __align__(16) float Bs[GK][GT + 4];
   const int b = blockIdx.z;
+  // D is symmetric by construction (same fp32 operations for (i,j) and (j,i)): only tiles on or above the diagonal
+  // are computed, each off-diagonal tile is also written transposed
+  if (blockIdx.x < blockIdx.y) return;
   const int i0 = blockIdx.y * GT, j0 = blockIdx.x * GT;
   const float* xb = x + static_cast<long long>(b) * N * C;
   const int tid = threadIdx.x;
@@ -95,6 +98,7 @@ __global__ void __launch_bounds__(256) gram_dist_kernel(const float* __restrict_
   }
   const float* nb = sqn + static_cast<long long>(b) * N;
   float* Db = D + static_cast<long long>(b) * N * N;
+  const bool mirror = blockIdx.x != blockIdx.y;
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
     const int i = i0 + ty * 4 + a;
@@ -105,7 +109,9 @@ __global__ void __launch_bounds__(256) gram_dist_kernel(const float* __restrict_
       const int j = j0 + tx * 4 + c;
       if (j >= N) continue;
       const float d2 = fmaf(-2.0f, acc[a][c], __fadd_rn(ni, nb[j]));
-      Db[static_cast<long long>(i) * N + j] = __fdiv_rn(sqrtf(fmaxf(d2, 0.f)), sqrtC);
+      const float d = __fdiv_rn(sqrtf(fmaxf(d2, 0.f)), sqrtC);
+      Db[static_cast<long long>(i) * N + j] = d;
+      if (mirror) Db[static_cast<long long>(j) * N + i] = d;
     }
   }
 }
