@@ -10,8 +10,9 @@
 //                 S = Q K_j^T   128 x nk (nk <= 64) x 64    -> TMEM columns [0, 64)
 //                 O += P_j V_j  128 x 64 x nk               -> TMEM columns [64, 128), V as MN-major operand
 //   warps 0..3  softmax, one thread per query row: tcgen05.ld S -> online softmax in the exp2 domain ->
-//               P (bf16) into a K-major 128B-swizzled smem tile -> rescale O in TMEM when the running max moved
-//               -> hand P to the MMA warp.  After the last chunk: O / l -> bf16 -> global.
+//               P (bf16 pairs) back into TMEM over the S columns (tcgen05.st; the P.V MMA takes its A operand from
+//               tensor memory) -> rescale O in TMEM when the running max moved -> hand over to the MMA warp.
+//               After the last chunk: O / l -> bf16 -> global.
 // Tensor-core work is issued in order, so "S_j complete" implies "P_{j-1} V_{j-1} complete": the single S and P
 // buffers need no further handshakes.  Latency is hidden across the three CTAs resident per SM.
 #include "common.cuh"
@@ -27,12 +28,12 @@ constexpr int OFF_Q = 0;                       // 128 x 64 bf16 = 16 KiB
 constexpr int KV_STAGES = 2;
 constexpr int OFF_K = 16384;                   // KV_STAGES x 8 KiB
 constexpr int OFF_V = OFF_K + KV_STAGES * KV_STAGE;
-constexpr int OFF_P = OFF_V + KV_STAGES * KV_STAGE;    // 128 x 64 bf16 = 16 KiB (one 64-key swizzle atom)
-constexpr int OFF_BARS = OFF_P + 16384;
+constexpr int OFF_BARS = OFF_V + KV_STAGES * KV_STAGE;
 constexpr int ATT_SMEM = OFF_BARS + 256;       // no alignment slack: the dynamic window starts 1 KiB aligned (checked)
 constexpr int ATT_THREADS = 192;
 constexpr int ATT_TMEM_COLS = 128;
 constexpr uint32_t O_COL = KT;
+constexpr uint32_t P_COL = 0;
 
 __device__ __forceinline__ float fast_exp2(float x) {   // MUFU.EX2; exp2(-inf) = 0, inputs here are <= 0
   float y;
@@ -41,7 +42,7 @@ __device__ __forceinline__ float fast_exp2(float x) {   // MUFU.EX2; exp2(-inf) 
 }
 
 // declared for 256 threads so ptxas caps registers at 128: two CTAs (6 warps each) then fit the per-SMSP register files
-__global__ void __launch_bounds__(ATT_THREADS, 3)
+__global__ void __launch_bounds__(ATT_THREADS, 4)
 attn_tcgen05_hd64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm_kv, bf16* __restrict__ out,
                          int T, int heads, int C, float scale_log2, long long* __restrict__ dbg) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -101,7 +102,7 @@ attn_tcgen05_hd64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_co
       // all operand descriptors are loop-invariant: build them once
       // (stage s of K/V only shifts the 14-bit address field by s * KV_STAGE / 16)
       const uint64_t dq0 = umma_desc_k_sw128(base + OFF_Q), dq1 = dq0 + 2, dq2 = dq0 + 4, dq3 = dq0 + 6;   // +32 B per k-step
-      const uint64_t dp0 = umma_desc_k_sw128(base + OFF_P), dp1 = dp0 + 2, dp2 = dp0 + 4, dp3 = dp0 + 6;
+      const uint32_t tp = tmem_base + P_COL;                 // P_j (bf16 pairs) overwrites the first half of the S columns
       const uint64_t dk0 = umma_desc_k_sw128(base + OFF_K), dk1 = dk0 + 2, dk2 = dk0 + 4, dk3 = dk0 + 6;
       const uint64_t dv0 = umma_desc_mn_sw128(base + OFF_V), dv1 = dv0 + 128, dv2 = dv0 + 256, dv3 = dv0 + 384;   // +2048 B
       const uint32_t idesc_pv = umma_idesc_bf16(QT, HD, true);
@@ -136,10 +137,10 @@ attn_tcgen05_hd64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_co
         const int st = j % KV_STAGES;
         const uint64_t soff = static_cast<uint64_t>(st * (KV_STAGE >> 4));
         if (elect_one_sync()) {
-          umma_f16(tmem_base + O_COL, dp0, dv0 + soff, idesc_pv, j != 0 ? 1u : 0u);
-          if (nk16 > 1) umma_f16(tmem_base + O_COL, dp1, dv1 + soff, idesc_pv, 1u);
-          if (nk16 > 2) umma_f16(tmem_base + O_COL, dp2, dv2 + soff, idesc_pv, 1u);
-          if (nk16 > 3) umma_f16(tmem_base + O_COL, dp3, dv3 + soff, idesc_pv, 1u);
+          umma_f16_ts(tmem_base + O_COL, tp, dv0 + soff, idesc_pv, j != 0 ? 1u : 0u);      // 16 keys = 8 TMEM columns per step
+          if (nk16 > 1) umma_f16_ts(tmem_base + O_COL, tp + 8, dv1 + soff, idesc_pv, 1u);
+          if (nk16 > 2) umma_f16_ts(tmem_base + O_COL, tp + 16, dv2 + soff, idesc_pv, 1u);
+          if (nk16 > 3) umma_f16_ts(tmem_base + O_COL, tp + 24, dv3 + soff, idesc_pv, 1u);
           umma_commit(kv_empty(st));
           if (j + 1 >= nchunks) umma_commit(o_final);
         }
@@ -154,77 +155,46 @@ attn_tcgen05_hd64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_co
     const bool warp_live = q0 + q * 32 < T;         // does this warp own any real query row?
     const uint32_t t_s = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t t_o = t_s + O_COL;
-    uint8_t* prow = smem + OFF_P + row * 128;
     float m = -INFINITY, l = 0.f;
     for (int j = 0; j < nchunks; ++j) {
       mbar_wait(s_full, j & 1);
       if (warp == 0 && lane == 0) TRACE(40 + 4 * j);
       tcgen05_fence_after();
       if (warp_live) {
-        const int valid = min(KT, T - j * KT);        // real keys in this chunk
-        const int nk = (valid + 15) & ~15;
-        float m_new, alpha, psum = 0.f;
-        if (valid == KT) {
-          // full chunk: S row (64 fp32) read from TMEM once and kept in registers for both passes
-          uint32_t r[KT];
-          tmem_ld_32x32b_x32(t_s, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
-          tmem_ld_32x32b_x32(t_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
-          tmem_ld_wait();
-          float mx0 = __uint_as_float(r[0]), mx1 = __uint_as_float(r[1]), mx2 = __uint_as_float(r[2]), mx3 = __uint_as_float(r[3]);
+        const int valid = min(KT, T - j * KT);        // real keys in this chunk (columns >= valid hold stale data)
+        float m_new, alpha, psum;
+        // S row (64 fp32) read from TMEM once; the probabilities are packed to bf16 pairs in place and stored back to
+        // TMEM over the first 32 S columns, where the P.V MMA reads them as its A operand (no trip through smem)
+        uint32_t r[KT];
+        tmem_ld_32x32b_x32(t_s, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+        tmem_ld_32x32b_x32(t_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+        tmem_ld_wait();
+        if (valid < KT) {
 #pragma unroll
-          for (int i = 4; i < KT; i += 4) {
-            mx0 = fmaxf(mx0, __uint_as_float(r[i])); mx1 = fmaxf(mx1, __uint_as_float(r[i + 1]));
-            mx2 = fmaxf(mx2, __uint_as_float(r[i + 2])); mx3 = fmaxf(mx3, __uint_as_float(r[i + 3]));
-          }
-          m_new = fmaxf(m, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2);
-          alpha = fast_exp2(m - m_new);
-          if (warp == 0 && lane == 0) TRACE(41 + 4 * j);
-          float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
-#pragma unroll
-          for (int g = 0; g < KT / 8; ++g) {
-            float pv[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) pv[i] = fast_exp2(fmaf(__uint_as_float(r[8 * g + i]), scale_log2, -m_new));
-            ps0 += pv[0] + pv[4]; ps1 += pv[1] + pv[5]; ps2 += pv[2] + pv[6]; ps3 += pv[3] + pv[7];
-            uint4 u;
-            u.x = pack_bf16x2(pv[0], pv[1]); u.y = pack_bf16x2(pv[2], pv[3]);
-            u.z = pack_bf16x2(pv[4], pv[5]); u.w = pack_bf16x2(pv[6], pv[7]);
-            *reinterpret_cast<uint4*>(prow + ((g ^ (row & 7)) << 4)) = u;
-          }
-          psum = (ps0 + ps1) + (ps2 + ps3);
-        } else {
-          // ragged last chunk: keys >= valid are masked to probability 0
-          float mx = -INFINITY;
-          for (int c0 = 0; c0 < nk; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(t_s + c0, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) if (c0 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
-          }
-          m_new = fmaxf(m, mx * scale_log2);
-          alpha = fast_exp2(m - m_new);
-          if (warp == 0 && lane == 0) TRACE(41 + 4 * j);
-          for (int c0 = 0; c0 < nk; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(t_s + c0, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float pv[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                pv[i] = (c0 + 8 * g + i < valid) ? fast_exp2(fmaf(__uint_as_float(r[8 * g + i]), scale_log2, -m_new)) : 0.f;
-                psum += pv[i];
-              }
-              const int chunk = (c0 >> 3) + g;
-              uint4 u;
-              u.x = pack_bf16x2(pv[0], pv[1]); u.y = pack_bf16x2(pv[2], pv[3]);
-              u.z = pack_bf16x2(pv[4], pv[5]); u.w = pack_bf16x2(pv[6], pv[7]);
-              *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) = u;
-            }
-          }
+          for (int i = 0; i < KT; ++i) if (i >= valid) r[i] = 0xff800000u;   // -inf -> probability 0
         }
+        float mx0 = __uint_as_float(r[0]), mx1 = __uint_as_float(r[1]), mx2 = __uint_as_float(r[2]), mx3 = __uint_as_float(r[3]);
+#pragma unroll
+        for (int i = 4; i < KT; i += 4) {
+          mx0 = fmaxf(mx0, __uint_as_float(r[i])); mx1 = fmaxf(mx1, __uint_as_float(r[i + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(r[i + 2])); mx3 = fmaxf(mx3, __uint_as_float(r[i + 3]));
+        }
+        m_new = fmaxf(m, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2);
+        alpha = fast_exp2(m - m_new);
+        if (warp == 0 && lane == 0) TRACE(41 + 4 * j);
+        float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
+#pragma unroll
+        for (int i = 0; i < KT; i += 4) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(r[i]), scale_log2, -m_new));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(r[i + 1]), scale_log2, -m_new));
+          const float p2 = fast_exp2(fmaf(__uint_as_float(r[i + 2]), scale_log2, -m_new));
+          const float p3 = fast_exp2(fmaf(__uint_as_float(r[i + 3]), scale_log2, -m_new));
+          ps0 += p0; ps1 += p1; ps2 += p2; ps3 += p3;
+          r[i / 2] = pack_bf16x2(p0, p1);               // in place: slots <= i/2+1 were consumed already
+          r[i / 2 + 1] = pack_bf16x2(p2, p3);
+        }
+        psum = (ps0 + ps1) + (ps2 + ps3);
+        tmem_st_32x32b_x32(t_s + P_COL, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
         l = l * alpha + psum;
         m = m_new;
         if (warp == 0 && lane == 0) TRACE(42 + 4 * j);
@@ -239,9 +209,8 @@ attn_tcgen05_hd64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_co
             for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
             tmem_st_32x32b_x32(t_o + c0, o);
           }
-          tmem_st_wait();
         }
-        fence_proxy_async_smem();
+        tmem_st_wait();
       }
       tcgen05_fence_before();
       __syncwarp();
