@@ -50,11 +50,20 @@ uint64_t setok_launch_count(void);
  *   m_dev       (device) optional int32: the live row count (rows >= *m_dev are skipped); M is then the
  *               capacity the buffers were sized for.  This is how ragged (data-dependent K) batches run
  *               without a host sync.
- *   K % 8 == 0, N % 8 == 0.
+ *   N % 4 == 0; K arbitrary (leading dimensions must still be multiples of 8 elements).
  */
 int setok_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* D, int64_t ldd,
                     int out_dtype, const float* bias, const void* residual, int64_t ldr, int residual_dtype,
                     int act, int M, int N, int K, const int32_t* m_dev, setok_stream_t stream);
+
+/* Batched form: `batch` independent products D_b = epilogue(A_b * W_b^T); operand b starts at base + b * stride
+ * (strides in elements).  With w_mn_major != 0, W_b is given as [K, N] row-major (N contiguous) instead of [N, K] —
+ * the form P.V takes in attention (W = V: keys x head_dim).  Used for the dense masked attention of the cluster
+ * encoder (src/model/setok/module.py:66-70 over all clusters of an image at once). */
+int setok_gemm_bf16_batched(const void* A, int64_t lda, int64_t a_batch_stride, const void* W, int64_t ldw,
+                            int64_t w_batch_stride, int w_mn_major, void* D, int64_t ldd, int64_t d_batch_stride,
+                            int out_dtype, const float* bias, int act, int batch, int M, int N, int K,
+                            setok_stream_t stream);
 
 /* Row LayerNorm (eps inside the sqrt, biased variance — torch.nn.LayerNorm).  in/out dtype f32|bf16.
  * gather (device, int32 [rows]) optionally picks the source row: out[r] = LN(in[gather[r]]). */

@@ -58,6 +58,8 @@ SIGNATURES = {
     "setok_launch_count": (C.c_uint64, []),
     "setok_gemm_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64,
                                 c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "setok_gemm_bf16_batched": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_int64, c_int,
+                                        c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "setok_layernorm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p,
                                 c_void_p, c_void_p]),
     "setok_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),

@@ -39,18 +39,38 @@ int check_vit(const setok_vit* v) {
   return SETOK_OK;
 }
 
-struct BlockBufs { bf16 *h, *qkv, *ao, *u; };
+struct BlockBufs { bf16 *h, *qkv, *ao, *u; float* S; bf16* P; };
 
 // Block.forward (reference module.py:95-100): depth x [x += Attn_i(norm1(x))], then x += Mlp(norm2(x)).
 // x is the fp32 residual stream over packed rows; attention is restricted to each row's segment.
+// dense_N > 0: the rows are dense_N-token images sorted by cluster (the per-cluster encoder).  Attention then runs as a
+// dense masked attention per image on the tensor cores -- S = Q K^T (batched GEMM), masked softmax over each row's
+// cluster range, O = P V (batched GEMM, V as MN-major operand) -- whose cost does not depend on the cluster sizes;
+// the warp-per-row kernel is kept for the ragged inter-cluster encoder, where segments are a handful of tokens.
 int run_block(const setok_block& blk, int C, int heads, int F, float* x, int rows_cap, const int32_t* m_dev,
-              const int32_t* seg_off, const int32_t* row_seg, const BlockBufs& w, cudaStream_t stream) {
+              const int32_t* seg_off, const int32_t* row_seg, const BlockBufs& w, cudaStream_t stream, int dense_N = 0) {
   const float scale = 1.0f / std::sqrt(static_cast<float>(C / heads));
+  const int hd = C / heads;
   for (int i = 0; i < blk.depth; ++i) {
     const setok_attn& at = blk.attn[i];
     SETOK_TRY(launch_layernorm(x, SETOK_F32, w.h, SETOK_BF16, blk.n1_g, blk.n1_b, 1e-5f, rows_cap, C, nullptr, m_dev, stream));
     SETOK_TRY(launch_gemm(GemmArgs{w.h, C, at.w_qkv, C, w.qkv, 3LL * C, SETOK_BF16, at.b_qkv, nullptr, 0, 0, SETOK_ACT_NONE, rows_cap, 3 * C, C, m_dev, 0}, stream));
-    SETOK_TRY(launch_attention(w.qkv, w.ao, rows_cap, C, heads, scale, seg_off, row_seg, 0, m_dev, stream));
+    if (dense_N > 0) {
+      const int N = dense_N, Bimg = rows_cap / N;
+      const int ldS = N, ldP = static_cast<int>(round_up(N, 8));
+      for (int h = 0; h < heads; ++h) {
+        GemmArgs sg{w.qkv + h * hd, 3LL * C, w.qkv + C + h * hd, 3LL * C, w.S, ldS, SETOK_F32, nullptr, nullptr, 0, 0, SETOK_ACT_NONE, N, N, hd, nullptr, 0};
+        sg.batch = Bimg; sg.a_batch_stride = 3LL * C * N; sg.w_batch_stride = 3LL * C * N; sg.d_batch_stride = static_cast<int64_t>(N) * ldS;
+        SETOK_TRY(launch_gemm(sg, stream));
+        SETOK_TRY(launch_masked_softmax(w.S, w.P, seg_off, row_seg, rows_cap, N, ldS, ldP, scale, stream));
+        GemmArgs pv{w.P, ldP, w.qkv + 2 * C + h * hd, 3LL * C, w.ao + h * hd, C, SETOK_BF16, nullptr, nullptr, 0, 0, SETOK_ACT_NONE, N, hd, N, nullptr, 0};
+        pv.batch = Bimg; pv.a_batch_stride = static_cast<int64_t>(N) * ldP; pv.w_batch_stride = 3LL * C * N; pv.d_batch_stride = static_cast<int64_t>(N) * C;
+        pv.w_mn_major = 1;
+        SETOK_TRY(launch_gemm(pv, stream));
+      }
+    } else {
+      SETOK_TRY(launch_attention(w.qkv, w.ao, rows_cap, C, heads, scale, seg_off, row_seg, 0, m_dev, stream));
+    }
     SETOK_TRY(launch_gemm(GemmArgs{w.ao, C, at.w_proj, C, x, C, SETOK_F32, at.b_proj, x, C, SETOK_F32, SETOK_ACT_NONE, rows_cap, C, C, m_dev, 0}, stream));
   }
   SETOK_TRY(launch_layernorm(x, SETOK_F32, w.h, SETOK_BF16, blk.n2_g, blk.n2_b, 1e-5f, rows_cap, C, nullptr, m_dev, stream));
@@ -83,6 +103,8 @@ void head_carve(const setok_head* hd, int B, int N, Arena& a, HeadBufs* o) {
   o->bb.qkv = a.take<bf16>(R * 3 * C);
   o->bb.ao = a.take<bf16>(R * C);
   o->bb.u = a.take<bf16>(R * hd->mlp);
+  o->bb.S = a.take<float>(R * static_cast<size_t>(N));
+  o->bb.P = a.take<bf16>(R * round_up(N, 8));
 }
 
 }  // namespace
@@ -169,7 +191,8 @@ extern "C" int setok_head_forward(const setok_head* hd, const float* x_pos, cons
   // segment; the Block's linear layers then run over all B*N rows at once and only attention is segmented.
   SETOK_TRY(launch_sort_by_cluster(idx_cluster, num_clusters, offsets, B, N, w.perm, w.row_seg, w.seg_off, stream));
   SETOK_TRY(launch_gather_rows(x_pos, w.xs, w.perm, R, C, stream));
-  SETOK_TRY(run_block(hd->inner, C, hd->heads, F, w.xs, R, nullptr, w.seg_off, w.row_seg, w.bb, stream));
+  const int dense_N = (N % 4 == 0 && N >= 64 && (C / hd->heads) % 8 == 0) ? N : 0;
+  SETOK_TRY(run_block(hd->inner, C, hd->heads, F, w.xs, R, nullptr, w.seg_off, w.row_seg, w.bb, stream, dense_N));
   SETOK_TRY(launch_segment_mean(w.xs, w.seg_off, n_tok, R, C, w.g, group_features, stream));       // tokenizer.py:151
 
   // inter_encoder over each image's K_b cluster tokens (tokenizer.py:179, repair R2), then `out` (:180)

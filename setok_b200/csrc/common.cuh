@@ -271,9 +271,10 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
   return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 // MN-major, 128-byte-swizzled operand: tile rows are K indices, each row holds 64 contiguous MN elements
-// (128 B); 8-row groups 1024 B apart (SBO); LBO (stride between 64-element MN atoms) unused for MN extent 64.
-__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
-  return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+// (128 B); 8-row groups 1024 B apart (SBO); LBO = byte stride between 64-element MN atoms (unused for MN extent 64).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes = 16) {
+  return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16) | (64ull << 32) |
+         (1ull << 46) | (2ull << 61);
 }
 // Instruction descriptor, kind::f16: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, A K-major,
 // B K-major unless b_mn_major (bit 16), N>>3 at [17,23), M>>4 at [24,29).
@@ -307,6 +308,12 @@ __device__ __forceinline__ void tma_load_2d_2sm(const void* tmap, uint32_t clust
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(cluster_bar_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(const void* tmap, uint32_t cluster_bar_addr, uint32_t smem_dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(cluster_bar_addr), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 template <int COLS>
@@ -363,6 +370,11 @@ struct GemmArgs {
   int M, N, K;
   const int32_t* m_dev;
   int remap_P;   // >0: patch-embed mode: out row r -> r + r/P + 1, residual row -> 1 + r%P (pos-emb broadcast)
+  // batched GEMM: `batch` independent problems, operand b at base + b * stride (elements).  bias is shared; no residual.
+  int batch = 1;
+  int64_t a_batch_stride = 0, w_batch_stride = 0, d_batch_stride = 0;
+  // W given as [K, N] row-major (N contiguous) instead of [N, K]: the MN-major B operand form (e.g. V in P.V)
+  int w_mn_major = 0;
 };
 int launch_gemm(const GemmArgs& g, cudaStream_t stream);
 

@@ -52,6 +52,9 @@ struct GemmDev {
   const int32_t* m_dev;
   int M, N, K;
   int act, out_f32, res_kind, remap_P;
+  int batch;
+  long long d_batch_stride;   // elements of D's type
+  int w_mn_major;
 };
 
 // Epilogue configuration is a template so the per-element code has no run-time branches; -1 = run time
@@ -101,7 +104,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   constexpr int TILE_M = BM * CG;
   const int tiles_m = (M_eff + TILE_M - 1) / TILE_M;
   const int tiles_n = (p.N + BN - 1) / BN;
-  const int num_tiles = tiles_m * tiles_n;
+  const int tiles_per_batch = tiles_m * tiles_n;
+  const int num_tiles = tiles_per_batch * p.batch;
   const int k_blocks = (p.K + BK - 1) / BK;
   const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;   // both CTAs of a pair walk the same tiles
 
@@ -109,21 +113,36 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int t = tile0; t < num_tiles; t += tile_step) {
-        const int m_blk = t / tiles_n, n_blk = t % tiles_n;
+        const int bt = t / tiles_per_batch, tt = t % tiles_per_batch;
+        const int m_blk = tt / tiles_n, n_blk = tt % tiles_n;
+        const int a_row = m_blk * TILE_M + static_cast<int>(rank) * BM;
+        const int b_row = n_blk * BN + static_cast<int>(rank) * (BN / CG);      // first N index this CTA stages
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = base + OFF_A + stage * A_STAGE_BYTES, sb = base + OFF_B + stage * B_STAGE_BYTES;
           if (CG == 2) {
             // both CTAs' bytes are counted on the LEADER's full barrier (the MMA issuer waits there).  The peer cannot
             // run a phase ahead: its empty barrier for this stage fires only after the MMAs that consumed the stage
             // retired, i.e. after the leader's full barrier already flipped.
             const uint32_t lead_full = mapa_shared(full_bar(stage), 0);
             if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
-            tma_load_2d_2sm(&tmA, lead_full, base + OFF_A + stage * A_STAGE_BYTES, kb * BK, m_blk * TILE_M + static_cast<int>(rank) * BM);
-            tma_load_2d_2sm(&tmB, lead_full, base + OFF_B + stage * B_STAGE_BYTES, kb * BK, n_blk * BN + static_cast<int>(rank) * (BN / 2));
+            tma_load_3d_2sm(&tmA, lead_full, sa, kb * BK, a_row, bt);
+            if (p.w_mn_major) {
+              // B tile = (BN/CG)/64 atoms of [64 K-rows x 64 N-columns]; global W is [K, N] (N contiguous)
+#pragma unroll
+              for (int at = 0; at < BN / CG / 64; ++at) tma_load_3d_2sm(&tmB, lead_full, sb + at * 8192, b_row + at * 64, kb * BK, bt);
+            } else {
+              tma_load_3d_2sm(&tmB, lead_full, sb, kb * BK, b_row, bt);
+            }
           } else {
             mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
-            tma_load_2d(&tmA, full_bar(stage), base + OFF_A + stage * A_STAGE_BYTES, kb * BK, m_blk * BM);
-            tma_load_2d(&tmB, full_bar(stage), base + OFF_B + stage * B_STAGE_BYTES, kb * BK, n_blk * BN);
+            tma_load_3d(&tmA, full_bar(stage), sa, kb * BK, a_row, bt);
+            if (p.w_mn_major) {
+#pragma unroll
+              for (int at = 0; at < BN / CG / 64; ++at) tma_load_3d(&tmB, full_bar(stage), sb + at * 8192, b_row + at * 64, kb * BK, bt);
+            } else {
+              tma_load_3d(&tmB, full_bar(stage), sb, kb * BK, b_row, bt);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -131,7 +150,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
   } else if (warp == W_MMA) {
     if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN);
+      const uint32_t idesc = umma_idesc_bf16(BM * CG, BN, p.w_mn_major != 0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int t = tile0; t < num_tiles; t += tile_step) {
@@ -146,7 +165,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t adesc = umma_desc_k_sw128(a_addr + k * UMMA_K * 2);
-            const uint64_t bdesc = umma_desc_k_sw128(b_addr + k * UMMA_K * 2);
+            // K-major B: +32 B per 16-wide k-step inside the 128 B row; MN-major B: +16 K-rows = 2048 B, atoms 8 KiB apart
+            const uint64_t bdesc = p.w_mn_major ? umma_desc_mn_sw128(b_addr + k * 2048, 8192) : umma_desc_k_sw128(b_addr + k * UMMA_K * 2);
             if (CG == 2) umma_f16_2cta(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
             else umma_f16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
           }
@@ -172,9 +192,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int rsub = lane >> 3;                   // row (mod 4) handled in the coalesced phase
     const float* bias = p.bias;
     for (int t = tile0; t < num_tiles; t += tile_step) {
-      const int m_blk = t / tiles_n, n_blk = t % tiles_n;
+      const int bt = t / tiles_per_batch, tt = t % tiles_per_batch;
+      const int m_blk = tt / tiles_n, n_blk = tt % tiles_n;
       const int row0 = m_blk * TILE_M + static_cast<int>(rank) * BM + q * 32;
       const int n0 = n_blk * BN + half * 128;
+      const long long dbase = static_cast<long long>(bt) * p.d_batch_stride;
       bool waited = false;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + half * 128);
       // bf16 residual (the ViT's out_proj / fc2): the whole tile's residual is requested before waiting for the
@@ -263,9 +285,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           if (grow < M_eff && col_ok) {
             const long long orow = remap_P > 0 ? (grow + grow / remap_P + 1) : grow;
             if (out_f32) {
-              *reinterpret_cast<float4*>(static_cast<float*>(p.D) + orow * p.ldd + col) = v;
+              *reinterpret_cast<float4*>(static_cast<float*>(p.D) + dbase + orow * p.ldd + col) = v;
             } else {
-              *reinterpret_cast<uint2*>(static_cast<bf16*>(p.D) + orow * p.ldd + col) =
+              *reinterpret_cast<uint2*>(static_cast<bf16*>(p.D) + dbase + orow * p.ldd + col) =
                   make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
             }
           }
@@ -308,19 +330,21 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int make_tmap_2d_bf16(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows) {
+// 3-D map over a batch of row-major bf16 matrices: dims {cols, rows, batch}; box {box_cols, box_rows, 1}; 128B swizzle.
+int make_tmap_bf16(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint64_t batch,
+                   uint64_t batch_stride_elems, uint32_t box_cols, uint32_t box_rows) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(SETOK_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (driver too old?)");
-  cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstr[1] = {ld_elems * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+  cuuint64_t gdim[3] = {cols, rows, batch};
+  cuuint64_t gstr[2] = {ld_elems * 2, (batch > 1 ? batch_stride_elems : rows * ld_elems) * 2};
+  cuuint32_t box[3] = {box_cols, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
-    return fail(SETOK_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu ld=%llu)", (int)r,
-                (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems);
+    return fail(SETOK_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu ld=%llu batch=%llu)", (int)r,
+                (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems, (unsigned long long)batch);
   return SETOK_OK;
 }
 
@@ -331,9 +355,15 @@ int g_gemm_cta_group = 0;   // 0 = automatic; 1 forces single-CTA tiles (debug /
 int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   SETOK_REQUIRE(g.A && g.W && g.D, SETOK_ERR_BAD_ARG, "gemm: null operand");
   SETOK_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, SETOK_ERR_BAD_ARG, "gemm: non-positive shape M=%d N=%d K=%d", g.M, g.N, g.K);
-  SETOK_REQUIRE(g.K % 8 == 0 && g.N % 8 == 0, SETOK_ERR_UNSUPPORTED, "gemm: K (%d) and N (%d) must be multiples of 8", g.K, g.N);
-  SETOK_REQUIRE(g.lda % 8 == 0 && g.ldw % 8 == 0 && g.lda >= g.K && g.ldw >= g.K, SETOK_ERR_BAD_ARG,
-                "gemm: lda/ldw must be multiples of 8 and >= K (lda=%lld ldw=%lld K=%d)", (long long)g.lda, (long long)g.ldw, g.K);
+  // K may be ragged (TMA zero-fills the tail of the last 64-wide K block); N only needs 4-column granularity
+  SETOK_REQUIRE(g.N % 4 == 0, SETOK_ERR_UNSUPPORTED, "gemm: N (%d) must be a multiple of 4", g.N);
+  SETOK_REQUIRE(g.lda % 8 == 0 && g.ldw % 8 == 0 && g.lda >= g.K && g.ldw >= (g.w_mn_major ? g.N : g.K), SETOK_ERR_BAD_ARG,
+                "gemm: lda/ldw must be multiples of 8 and cover a row (lda=%lld ldw=%lld K=%d N=%d)", (long long)g.lda, (long long)g.ldw, g.K, g.N);
+  SETOK_REQUIRE(g.batch >= 1, SETOK_ERR_BAD_ARG, "gemm: batch must be >= 1");
+  if (g.batch > 1) {
+    SETOK_REQUIRE(g.a_batch_stride % 8 == 0 && g.w_batch_stride % 8 == 0 && g.d_batch_stride % 4 == 0, SETOK_ERR_BAD_ARG, "gemm: batch strides must keep 16-byte alignment");
+    SETOK_REQUIRE(!g.residual && !g.m_dev && g.remap_P == 0, SETOK_ERR_UNSUPPORTED, "gemm: batched form takes no residual / device row count / remap");
+  }
   SETOK_REQUIRE(aligned16(g.A) && aligned16(g.W) && aligned16(g.D), SETOK_ERR_BAD_ARG, "gemm: operands must be 16-byte aligned");
   SETOK_REQUIRE(g.ldd % 4 == 0 && g.ldd >= g.N, SETOK_ERR_BAD_ARG, "gemm: ldd (%lld) must be a multiple of 4 and >= N", (long long)g.ldd);
   SETOK_REQUIRE(g.out_dtype == SETOK_F32 || g.out_dtype == SETOK_BF16, SETOK_ERR_BAD_ARG, "gemm: bad out_dtype %d", g.out_dtype);
@@ -349,7 +379,7 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   const int out_f32 = g.out_dtype == SETOK_F32 ? 1 : 0;
   // specialised epilogues for the combinations the tokenizer path launches; everything else -> generic
   // CTA pairs whenever there is at least one full 256-row tile; single CTAs for short row counts
-  const int cg = (g.M >= 256 && g_gemm_cta_group != 1) ? 2 : 1;
+  const int cg = (g.M >= 160 && g_gemm_cta_group != 1) ? 2 : 1;
 #define SETOK_PICK(A, R, O, P) (cg == 2 ? gemm_bf16_tcgen05_kernel<2, A, R, O, P> : gemm_bf16_tcgen05_kernel<1, A, R, O, P>)
   KernelFn fn = SETOK_PICK(-1, -1, -1, -1);
   if (g.remap_P == 0) {
@@ -374,14 +404,18 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
     }
   }
   CUtensorMap tmA, tmB;
-  SETOK_TRY(make_tmap_2d_bf16(&tmA, g.A, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)g.lda, BM));
-  SETOK_TRY(make_tmap_2d_bf16(&tmB, g.W, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldw, BN / cg));
+  SETOK_TRY(make_tmap_bf16(&tmA, g.A, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)g.lda, (uint64_t)g.batch, (uint64_t)g.a_batch_stride, BK, BM));
+  if (g.w_mn_major)   // W is [K, N]: box = 64 N-columns (128 B) x 64 K-rows, one per 64-column atom of the B tile
+    SETOK_TRY(make_tmap_bf16(&tmB, g.W, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.ldw, (uint64_t)g.batch, (uint64_t)g.w_batch_stride, 64, BK));
+  else
+    SETOK_TRY(make_tmap_bf16(&tmB, g.W, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldw, (uint64_t)g.batch, (uint64_t)g.w_batch_stride, BK, BN / cg));
   GemmDev p;
   p.D = g.D; p.ldd = g.ldd; p.bias = g.bias; p.res = g.residual; p.ldr = g.ldr; p.m_dev = g.m_dev;
   p.M = g.M; p.N = g.N; p.K = g.K; p.act = g.act; p.out_f32 = g.out_dtype == SETOK_F32;
   p.res_kind = res_kind;
   p.remap_P = g.remap_P;
-  const int tiles = ceil_div(g.M, BM * cg) * ceil_div(g.N, BN);
+  p.batch = g.batch; p.d_batch_stride = g.d_batch_stride; p.w_mn_major = g.w_mn_major;
+  const int tiles = ceil_div(g.M, BM * cg) * ceil_div(g.N, BN) * g.batch;
   const int max_groups = num_sms() / cg;
   const int grid = (tiles < max_groups ? tiles : max_groups) * cg;
   cudaLaunchConfig_t cfg{};
@@ -405,6 +439,15 @@ extern "C" int setok_gemm_bf16(const void* A, int64_t lda, const void* W, int64_
                                const float* bias, const void* residual, int64_t ldr, int residual_dtype, int act, int M,
                                int N, int K, const int32_t* m_dev, setok_stream_t stream) {
   setok::GemmArgs g{A, lda, W, ldw, D, ldd, out_dtype, bias, residual, ldr, residual_dtype, act, M, N, K, m_dev, 0};
+  return setok::launch_gemm(g, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int setok_gemm_bf16_batched(const void* A, int64_t lda, int64_t a_batch_stride, const void* W, int64_t ldw, int64_t w_batch_stride,
+                                       int w_mn_major, void* D, int64_t ldd, int64_t d_batch_stride, int out_dtype, const float* bias,
+                                       int act, int batch, int M, int N, int K, setok_stream_t stream) {
+  setok::GemmArgs g{A, lda, W, ldw, D, ldd, out_dtype, bias, nullptr, 0, 0, act, M, N, K, nullptr, 0};
+  g.batch = batch; g.a_batch_stride = a_batch_stride; g.w_batch_stride = w_batch_stride; g.d_batch_stride = d_batch_stride;
+  g.w_mn_major = w_mn_major;
   return setok::launch_gemm(g, static_cast<cudaStream_t>(stream));
 }
 

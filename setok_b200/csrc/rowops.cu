@@ -259,6 +259,33 @@ __global__ void __launch_bounds__(256) convert_rows_kernel(const TI* __restrict_
   }
 }
 
+// Dense cluster attention, middle step: P[r, :] = softmax(scale * S[r, keys of r's cluster]) and 0 elsewhere.
+// Rows are sorted by cluster, so the admissible keys of row r are the contiguous range of its segment.  One warp per row.
+__global__ void __launch_bounds__(256) masked_softmax_kernel(const float* __restrict__ S, bf16* __restrict__ P,
+                                                             const int32_t* __restrict__ seg_off, const int32_t* __restrict__ row_seg,
+                                                             int rows, int N, int ldS, int ldP, float scale_log2) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
+    const int img0 = (r / N) * N;
+    const int g = row_seg[r];
+    const int k0 = seg_off[g] - img0, k1 = seg_off[g + 1] - img0;
+    const float* s = S + static_cast<long long>(r) * ldS;
+    bf16* p = P + static_cast<long long>(r) * ldP;
+    float mx = -INFINITY;
+    for (int j = k0 + lane; j < k1; j += 32) mx = fmaxf(mx, s[j]);
+    mx = warp_max(mx) * scale_log2;
+    float sum = 0.f;
+    for (int j = k0 + lane; j < k1; j += 32) sum += exp2f(fmaf(s[j], scale_log2, -mx));
+    const float inv = 1.0f / warp_sum(sum);
+    for (int j = lane; j < ldP; j += 32) {
+      float v = 0.f;
+      if (j >= k0 && j < k1) v = exp2f(fmaf(s[j], scale_log2, -mx)) * inv;
+      p[j] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
 inline int grid_for(long long work_items, int threads, int max_waves = 8) {
   long long blocks = (work_items + threads - 1) / threads;
   const long long cap = static_cast<long long>(num_sms()) * max_waves;
@@ -285,6 +312,16 @@ int launch_layernorm(const void* in, int in_dtype, void* out, int out_dtype, con
   else if (in_dtype == SETOK_BF16 && out_dtype == SETOK_F32) LN_CASE(bf16, float);
   else return fail(SETOK_ERR_BAD_ARG, "layernorm: bad dtypes %d -> %d", in_dtype, out_dtype);
 #undef LN_CASE
+  SETOK_LAUNCH_CHECK();
+  return SETOK_OK;
+}
+
+int launch_masked_softmax(const float* S, void* P, const int32_t* seg_off, const int32_t* row_seg, int rows, int N, int ldS, int ldP,
+                          float scale, cudaStream_t stream) {
+  int grid = ceil_div(rows, 8);
+  const int cap = num_sms() * 16;
+  if (grid > cap) grid = cap;
+  masked_softmax_kernel<<<grid, 256, 0, stream>>>(S, static_cast<bf16*>(P), seg_off, row_seg, rows, N, ldS, ldP, scale * 1.4426950408889634f);
   SETOK_LAUNCH_CHECK();
   return SETOK_OK;
 }

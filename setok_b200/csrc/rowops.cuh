@@ -15,5 +15,7 @@ int launch_image_segments(const int32_t* offsets, int B, int32_t* row_seg, cudaS
 int launch_convert(const void* in, int in_dtype, void* out, int out_dtype, long long n, cudaStream_t stream);
 int launch_convert_rows(const void* in, int in_dtype, void* out, int out_dtype, int rows, int C, int act, const int32_t* m_dev,
                         cudaStream_t stream);
+int launch_masked_softmax(const float* S, void* P, const int32_t* seg_off, const int32_t* row_seg, int rows, int N, int ldS, int ldP,
+                          float scale, cudaStream_t stream);
 int get_pos_table(int h, int w, int C, const float** out, cudaStream_t stream);
 }  // namespace setok

@@ -76,6 +76,24 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     return out
 
 
+def gemm_batched(a: torch.Tensor, w: torch.Tensor, *, w_mn_major: bool = False, out_dtype=torch.bfloat16, bias: Optional[torch.Tensor] = None,
+                 act: int = ACT_NONE) -> torch.Tensor:
+    """a (B, M, K) bf16 (row stride may exceed K); w (B, N, K) or, with w_mn_major, (B, K, N).  Returns (B, M, N)."""
+    if a.dtype != torch.bfloat16 or w.dtype != torch.bfloat16 or a.dim() != 3 or w.dim() != 3:
+        raise SetokError("gemm_batched needs 3-D bfloat16 operands")
+    if not a.is_cuda or a.stride(2) != 1 or w.stride(2) != 1:
+        raise SetokError("gemm_batched needs CUDA operands with a unit innermost stride")
+    dev = a.device
+    Bt, M, K = a.shape
+    N = w.shape[2] if w_mn_major else w.shape[1]
+    out = torch.empty(Bt, M, N, dtype=out_dtype, device=dev)
+    with torch.cuda.device(dev):
+        st = _lib.load().setok_gemm_bf16_batched(a.data_ptr(), a.stride(1), a.stride(0), w.data_ptr(), w.stride(1), w.stride(0), int(w_mn_major),
+                                                 out.data_ptr(), out.stride(1), out.stride(0), _dt(out), _p(bias), act, Bt, M, N, K, _stream(dev))
+    check(st, "setok_gemm_bf16_batched")
+    return out
+
+
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5, *, out_dtype=torch.bfloat16,
               gather: Optional[torch.Tensor] = None, m_dev: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     dev = _dev(x, gamma, beta, gather, m_dev, out)

@@ -40,7 +40,7 @@ def test_argument_validation_without_gpu(lib):
     assert b"null" in lib.setok_last_error()
     buf = (C.c_char * 64)()
     p = C.addressof(buf) // 16 * 16 + 16
-    assert lib.setok_gemm_bf16(p, 8, p, 8, p, 8, 0, None, None, 0, 0, 0, 4, 8, 7, None, None) == -2     # K % 8
+    assert lib.setok_gemm_bf16(p, 8, p, 8, p, 8, 0, None, None, 0, 0, 0, 4, 6, 8, None, None) == -2     # N % 4
     assert lib.setok_layernorm(p, 0, p, 0, p, p, 1e-5, 4, 6, None, None, None) == -2                  # C % 4
     assert lib.setok_attention(p, p, 4, 24, 5, 1.0, None, None, 0, None, None) == -1                  # C % heads
     assert lib.setok_vit_workspace_bytes(None, 4) == 0

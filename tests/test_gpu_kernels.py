@@ -155,3 +155,25 @@ def test_attention_vit_hd64(T, B, heads):
     so = torch.arange(0, B * T + 1, T, dtype=torch.int32)
     out = ops.attention(qkv, heads, 0.125, uniform_T=T)
     _close(out, _attn_ref(qkv, heads, 0.125, so), 6e-3, "vit attention")
+
+
+@pytest.mark.parametrize("Bt,M,N,K,mn", [(3, 256, 256, 512, False), (5, 196, 196, 384, False), (4, 256, 512, 256, True), (3, 196, 384, 196, True), (2, 576, 512, 576, True),
+                                         (2, 100, 64, 72, True), (1, 300, 264, 128, False)])
+def test_gemm_batched_and_mn_major(Bt, M, N, K, mn):
+    """Batched products with strided operands (views into a packed qkv buffer) and the [K, N] (MN-major) B form."""
+    g = torch.Generator().manual_seed(Bt * 1000 + M + N + K)
+    pad = 24 + (-K % 8)                                          # leading dimensions stay multiples of 8 elements
+    a_full = torch.randn(Bt, M, K + pad, generator=g).to(DEV, torch.bfloat16)
+    a = a_full[:, :, 8:8 + K]                                     # row stride K+pad, 16-byte aligned start
+    if mn:
+        w_full = (torch.randn(Bt, K, N + 24 + (-N % 8), generator=g) * K ** -0.5).to(DEV, torch.bfloat16)
+        w = w_full[:, :, 16:16 + N]
+        ref = torch.bmm(a.float(), w.float())
+    else:
+        w_full = (torch.randn(Bt, N, K + pad, generator=g) * K ** -0.5).to(DEV, torch.bfloat16)
+        w = w_full[:, :, 8:8 + K]
+        ref = torch.bmm(a.float(), w.float().transpose(1, 2))
+    out = ops.gemm_batched(a, w, w_mn_major=mn, out_dtype=torch.float32)
+    _close(out, ref, 1e-4, f"batched gemm mn={mn}")
+    out = ops.gemm_batched(a, w, w_mn_major=mn, out_dtype=torch.bfloat16)
+    _close(out, ref, 5e-3, f"batched gemm bf16 mn={mn}")
