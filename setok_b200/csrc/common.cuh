@@ -372,7 +372,7 @@ struct GemmArgs {
   int remap_P;   // >0: patch-embed mode: out row r -> r + r/P + 1, residual row -> 1 + r%P (pos-emb broadcast)
   // batched GEMM: `batch` independent problems, operand b at base + b * stride (elements).  bias is shared; no residual.
   int batch = 1;
-  int64_t a_batch_stride = 0, w_batch_stride = 0, d_batch_stride = 0;
+  int64_t a_batch_stride = 0, w_batch_stride = 0, d_batch_stride = 0, r_batch_stride = 0;
   // W given as [K, N] row-major (N contiguous) instead of [N, K]: the MN-major B operand form (e.g. V in P.V)
   int w_mn_major = 0;
 };

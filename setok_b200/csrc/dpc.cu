@@ -22,12 +22,14 @@
 #include <vector>
 
 namespace setok {
+extern int g_dpc_tensor_gram;
 namespace {
 
 // ---- 1. x_pos = feats + pos; sqnorm ------------------------------------------------------------------
 template <class TI>
 __global__ void __launch_bounds__(256) posadd_sqnorm_kernel(const TI* __restrict__ feats, const float* __restrict__ pos,
-                                                            float* __restrict__ x_pos, float* __restrict__ sqn, int B, int N, int C) {
+                                                            float* __restrict__ x_pos, float* __restrict__ sqn, int B, int N, int C,
+                                                            bf16* __restrict__ xh, bf16* __restrict__ xl) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const long long rows = static_cast<long long>(B) * N;
@@ -46,6 +48,14 @@ __global__ void __launch_bounds__(256) posadd_sqnorm_kernel(const TI* __restrict
       const float4 p = __ldg(reinterpret_cast<const float4*>(pos + static_cast<long long>(t) * C + c));
       v.x = __fadd_rn(v.x, p.x); v.y = __fadd_rn(v.y, p.y); v.z = __fadd_rn(v.z, p.z); v.w = __fadd_rn(v.w, p.w);
       *reinterpret_cast<float4*>(x_pos + r * C + c) = v;
+      if (xh != nullptr) {
+        // x = hi + lo + O(2^-17 |x|) with hi, lo both bf16: the Gram then runs on the bf16 tensor cores with exact
+        // products (hi.hi + hi.lo + lo.hi + lo.lo) and fp32 accumulation
+        const uint32_t h0 = pack_bf16x2(v.x, v.y), h1 = pack_bf16x2(v.z, v.w);
+        const float2 a = unpack_bf16x2(h0), b2 = unpack_bf16x2(h1);
+        *reinterpret_cast<uint2*>(xh + r * C + c) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(xl + r * C + c) = make_uint2(pack_bf16x2(v.x - a.x, v.y - a.y), pack_bf16x2(v.z - b2.x, v.w - b2.y));
+      }
       s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
     }
     s = warp_sum(s);
@@ -113,6 +123,18 @@ __global__ void __launch_bounds__(256) gram_dist_kernel(const float* __restrict_
       Db[static_cast<long long>(i) * N + j] = d;
       if (mirror) Db[static_cast<long long>(j) * N + i] = d;
     }
+  }
+}
+
+// G (x_i . x_j, from the tensor-core path) -> D in place, same formula as gram_dist_kernel's epilogue
+__global__ void __launch_bounds__(256) gram_to_dist_kernel(float* __restrict__ D, const float* __restrict__ sqn, int N, float sqrtC, long long total) {
+  const long long nn = static_cast<long long>(N) * N;
+  for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long b = e / nn;
+    const int i = static_cast<int>((e % nn) / N), j = static_cast<int>(e % N);
+    const float* nb = sqn + b * N;
+    const float d2 = fmaf(-2.0f, D[e], __fadd_rn(nb[i], nb[j]));
+    D[e] = __fdiv_rn(sqrtf(fmaxf(d2, 0.f)), sqrtC);
   }
 }
 
@@ -329,15 +351,20 @@ int get_pos_table(int h, int w, int C, const float** out, cudaStream_t stream) {
   return SETOK_OK;
 }
 
+int g_dpc_tensor_gram = 1;   // 0 forces the fp32-FMA Gram kernel (A/B via setok_debug_set_dpc_tensor_gram)
+
 }  // namespace setok
 
 using namespace setok;
 
+extern "C" void setok_debug_set_dpc_tensor_gram(int on) { g_dpc_tensor_gram = on; }
+
 extern "C" size_t setok_dpc_workspace_bytes(int B, int N, int C) {
-  (void)C;
   Arena a(nullptr, 0);
   a.take<float>(static_cast<size_t>(B) * N);          // squared norms
   a.take<float>(static_cast<size_t>(B) * N * N);      // distance matrices
+  a.take<bf16>(static_cast<size_t>(B) * N * C);       // bf16 split of x_pos: hi
+  a.take<bf16>(static_cast<size_t>(B) * N * C);       //                      lo
   return a.off;
 }
 
@@ -359,6 +386,10 @@ extern "C" int setok_dpc_cluster_pos(const void* feats, int feat_dtype, const fl
   Arena a(workspace, workspace_bytes);
   float* sqn = a.take<float>(static_cast<size_t>(B) * N);
   float* D = a.take<float>(static_cast<size_t>(B) * N * N);
+  bf16* xh = a.take<bf16>(static_cast<size_t>(B) * N * C);
+  bf16* xl = a.take<bf16>(static_cast<size_t>(B) * N * C);
+  // Gram on the tensor cores when the shapes allow the batched GEMM (leading dimensions multiples of 8 / 4)
+  const bool tensor_gram = (C % 8 == 0) && (N % 4 == 0) && g_dpc_tensor_gram;
   const float* pos = pos_table;
   if (pos == nullptr) SETOK_TRY(get_pos_table(h, w, C, &pos, stream));
   SETOK_REQUIRE(aligned16(pos), SETOK_ERR_BAD_ARG, "dpc_cluster: pos table must be 16-byte aligned");
@@ -366,15 +397,34 @@ extern "C" int setok_dpc_cluster_pos(const void* feats, int feat_dtype, const fl
   const long long rows = static_cast<long long>(B) * N;
   int grid = static_cast<int>((rows + 7) / 8);
   if (grid > num_sms() * 16) grid = num_sms() * 16;
-  if (feat_dtype == SETOK_F32) posadd_sqnorm_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(feats), pos, x_pos, sqn, B, N, C);
-  else if (feat_dtype == SETOK_BF16) posadd_sqnorm_kernel<bf16><<<grid, 256, 0, stream>>>(static_cast<const bf16*>(feats), pos, x_pos, sqn, B, N, C);
+  bf16* oh = tensor_gram ? xh : nullptr;
+  bf16* ol = tensor_gram ? xl : nullptr;
+  if (feat_dtype == SETOK_F32) posadd_sqnorm_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(feats), pos, x_pos, sqn, B, N, C, oh, ol);
+  else if (feat_dtype == SETOK_BF16) posadd_sqnorm_kernel<bf16><<<grid, 256, 0, stream>>>(static_cast<const bf16*>(feats), pos, x_pos, sqn, B, N, C, oh, ol);
   else return fail(SETOK_ERR_BAD_ARG, "dpc_cluster: bad feature dtype %d", feat_dtype);
   SETOK_LAUNCH_CHECK();
 
   const float sqrtC = static_cast<float>(std::sqrt(static_cast<double>(C)));
-  dim3 ggrid(ceil_div(N, GT), ceil_div(N, GT), B);
-  gram_dist_kernel<<<ggrid, 256, 0, stream>>>(x_pos, sqn, D, N, C, sqrtC);
-  SETOK_LAUNCH_CHECK();
+  if (tensor_gram) {
+    // G = hi hi^T + hi lo^T + lo hi^T + lo lo^T: four batched tcgen05 GEMMs accumulating in fp32 through the residual input
+    const bf16* lhs[4] = {xh, xh, xl, xl};
+    const bf16* rhs[4] = {xh, xl, xh, xl};
+    for (int t = 0; t < 4; ++t) {
+      GemmArgs g{lhs[t], C, rhs[t], C, D, N, SETOK_F32, nullptr, t ? D : nullptr, N, SETOK_F32, SETOK_ACT_NONE, N, N, C, nullptr, 0};
+      g.batch = B; g.a_batch_stride = static_cast<int64_t>(N) * C; g.w_batch_stride = static_cast<int64_t>(N) * C;
+      g.d_batch_stride = static_cast<int64_t>(N) * N; g.r_batch_stride = static_cast<int64_t>(N) * N;
+      SETOK_TRY(launch_gemm(g, stream));
+    }
+    const long long total = static_cast<long long>(B) * N * N;
+    long long blocks = (total + 255) / 256;
+    if (blocks > num_sms() * 16LL) blocks = num_sms() * 16LL;
+    gram_to_dist_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(D, sqn, N, sqrtC, total);
+    SETOK_LAUNCH_CHECK();
+  } else {
+    dim3 ggrid(ceil_div(N, GT), ceil_div(N, GT), B);
+    gram_dist_kernel<<<ggrid, 256, 0, stream>>>(x_pos, sqn, D, N, C, sqrtC);
+    SETOK_LAUNCH_CHECK();
+  }
 
   if (N <= 256) dpc_select_kernel<8><<<B, SEL_THREADS, 0, stream>>>(D, noise, token_mask, N, k, threshold, min_cluster_num, idx_cluster, score, index_down, num_clusters);
   else if (N <= 576) dpc_select_kernel<18><<<B, SEL_THREADS, 0, stream>>>(D, noise, token_mask, N, k, threshold, min_cluster_num, idx_cluster, score, index_down, num_clusters);

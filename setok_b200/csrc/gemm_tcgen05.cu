@@ -54,6 +54,7 @@ struct GemmDev {
   int act, out_f32, res_kind, remap_P;
   int batch;
   long long d_batch_stride;   // elements of D's type
+  long long r_batch_stride;   // elements of the residual's type
   int w_mn_major;
 };
 
@@ -212,7 +213,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             const int grow = row0 + it * 4 + rsub;
             rt[ch][it] = make_uint2(0u, 0u);
             if (grow < M_eff && col < p.N)
-              rt[ch][it] = *reinterpret_cast<const uint2*>(static_cast<const bf16*>(p.res) + static_cast<long long>(grow) * p.ldr + col);
+              rt[ch][it] = *reinterpret_cast<const uint2*>(static_cast<const bf16*>(p.res) + static_cast<long long>(bt) * p.r_batch_stride + static_cast<long long>(grow) * p.ldr + col);
           }
         }
       }
@@ -235,7 +236,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             rb[it] = make_uint2(0u, 0u);
             if (grow < M_eff && col_ok) {
               const long long rrow = remap_P > 0 ? (1 + grow % remap_P) : grow;
-              rb[it] = *reinterpret_cast<const uint2*>(static_cast<const bf16*>(p.res) + rrow * p.ldr + col);
+              rb[it] = *reinterpret_cast<const uint2*>(static_cast<const bf16*>(p.res) + static_cast<long long>(bt) * p.r_batch_stride + rrow * p.ldr + col);
             }
           }
         } else if (res_kind == 2) {
@@ -245,7 +246,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             rf[it] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (grow < M_eff && col_ok) {
               const long long rrow = remap_P > 0 ? (1 + grow % remap_P) : grow;
-              rf[it] = *reinterpret_cast<const float4*>(static_cast<const float*>(p.res) + rrow * p.ldr + col);
+              rf[it] = *reinterpret_cast<const float4*>(static_cast<const float*>(p.res) + static_cast<long long>(bt) * p.r_batch_stride + rrow * p.ldr + col);
             }
           }
         }
@@ -362,7 +363,7 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   SETOK_REQUIRE(g.batch >= 1, SETOK_ERR_BAD_ARG, "gemm: batch must be >= 1");
   if (g.batch > 1) {
     SETOK_REQUIRE(g.a_batch_stride % 8 == 0 && g.w_batch_stride % 8 == 0 && g.d_batch_stride % 4 == 0, SETOK_ERR_BAD_ARG, "gemm: batch strides must keep 16-byte alignment");
-    SETOK_REQUIRE(!g.residual && !g.m_dev && g.remap_P == 0, SETOK_ERR_UNSUPPORTED, "gemm: batched form takes no residual / device row count / remap");
+    SETOK_REQUIRE(!g.m_dev && g.remap_P == 0 && g.r_batch_stride % 4 == 0, SETOK_ERR_UNSUPPORTED, "gemm: batched form takes no device row count / remap");
   }
   SETOK_REQUIRE(aligned16(g.A) && aligned16(g.W) && aligned16(g.D), SETOK_ERR_BAD_ARG, "gemm: operands must be 16-byte aligned");
   SETOK_REQUIRE(g.ldd % 4 == 0 && g.ldd >= g.N, SETOK_ERR_BAD_ARG, "gemm: ldd (%lld) must be a multiple of 4 and >= N", (long long)g.ldd);
@@ -414,7 +415,7 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   p.M = g.M; p.N = g.N; p.K = g.K; p.act = g.act; p.out_f32 = g.out_dtype == SETOK_F32;
   p.res_kind = res_kind;
   p.remap_P = g.remap_P;
-  p.batch = g.batch; p.d_batch_stride = g.d_batch_stride; p.w_mn_major = g.w_mn_major;
+  p.batch = g.batch; p.d_batch_stride = g.d_batch_stride; p.r_batch_stride = g.r_batch_stride; p.w_mn_major = g.w_mn_major;
   const int tiles = ceil_div(g.M, BM * cg) * ceil_div(g.N, BN) * g.batch;
   const int max_groups = num_sms() / cg;
   const int grid = (tiles < max_groups ? tiles : max_groups) * cg;

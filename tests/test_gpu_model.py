@@ -110,7 +110,7 @@ def test_head_golden():
         Kb = T(g[f"img{b}/index_down"]).numel()
         assert rt[b].shape == (Kb, Ctok)
         assert torch.equal(rt.index_down[b, :Kb].cpu(), T(g[f"img{b}/index_down"]))
-        torch.testing.assert_close(score[b].cpu(), T(g[f"img{b}/score"]), rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(score[b].cpu(), T(g[f"img{b}/score"]), rtol=1e-3, atol=1e-5)   # cancelling cdist form, see test_gpu_dpc
         mx, fro = _err(gf[b], T(g[f"img{b}/group_features"]))
         assert fro < 1e-2 and mx < 2e-2, ("group_features", b, mx, fro)
         mx, fro = _err(rt[b], T(g[f"img{b}/tokens"]))
