@@ -210,6 +210,21 @@ def time_gemm_mix(dev, layers_run, reps=2):
     return ms / launches, flops / launches, flops / (ms * 1e-3) / 1e12
 
 
+def time_tower(tok, images, reps=5):
+    """The ViT tower alone (a1+a2) on the bench batch: CUDA events around `reps` forwards."""
+    dev = images.device
+    for _ in range(2):
+        tok.image_feature_encoder(images)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        tok.image_feature_encoder(images)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    return e0.elapsed_time(e1) / reps
+
+
 def time_cluster(dev, reps=10):
     """Clustering (pos add + DPC-kNN, a3+a4) on feature-injected mixtures: achieved algorithmic HBM GB/s."""
     from setok_b200 import ops
@@ -323,6 +338,8 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     pk = peaks()
+    vit_ms = time_tower(tok, images)
+    vit_tf = BATCH * vit_flops_per_image(layers_run) / (vit_ms * 1e-3) / 1e12
     cl_ms, cl_bytes, cl_gbs, kstats = time_cluster(dev, reps=20)
     gemm_ms, gemm_flops, gemm_tf = time_gemm_mix(dev, layers_run)
     step_ms = ms / args.steps
@@ -341,6 +358,9 @@ def run_ours(args):
                      "peak_source": f"{pk['src']} sustained bf16 (kernel timed inside a long loop)",
                      "step_share": (4 * layers_run * gemm_ms) / step_ms,
                      "vit_tensor_frac_of_step": (BATCH * vit_flops_per_image(layers_run) / (step_ms * 1e-3) / 1e12) / pk["tf_sustained"]},
+        "roofline_vit": {"kernel": "whole ViT-L/14 tower (im2col, patch GEMM, 23 x [LN, qkv, attention, out_proj, LN, fc1, fc2])", "bound": "tensor",
+                         "achieved": vit_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": vit_tf / pk["tf_sustained"],
+                         "ms": vit_ms, "flops": BATCH * vit_flops_per_image(layers_run)},
         "roofline_cluster": {"kernel": "posadd_sqnorm + gram_dist + dpc_select (a3+a4), B=256 N=256 C=1024 feature-injected", "bound": "hbm",
                              "achieved": cl_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": cl_gbs / pk["hbm"], "traffic": NCU_CLUSTER_DRAM_BYTES_PER_LAUNCH,
                              "bytes_per_launch": cl_bytes, "ms_per_launch": cl_ms, "k_min_mean_max": kstats,
