@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsetok_b200.so")
+LIB_PATH = os.environ.get("SETOK_B200_LIB") or os.path.join(HERE, "libsetok_b200.so")   # override: A/B builds under tools/
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_QUICK_GELU, ACT_GELU_ERF = 0, 1, 2

@@ -385,6 +385,12 @@ struct GemmArgs {
 };
 int launch_gemm(const GemmArgs& g, cudaStream_t stream);
 
+// dpc_fused.cu: whole clustering (a3+a4) in one persistent kernel for N <= 256
+bool dpc_fused_supported(int N, int C, int k);
+int launch_dpc_fused(const void* feats, int feat_dtype, const float* pos, const float* noise, const float* token_mask, int B, int N, int C,
+                     int k, float threshold, int min_cluster_num, float* x_pos, int64_t* idx_cluster, float* score, int64_t* index_down,
+                     int32_t* num_clusters, cudaStream_t stream);
+
 int launch_layernorm(const void* in, int in_dtype, void* out, int out_dtype, const float* gamma, const float* beta,
                      float eps, int rows, int C, const int32_t* gather, const int32_t* m_dev, cudaStream_t stream);
 int launch_attention_tcgen05(const void* qkv, void* out, int B, int T, int C, int heads, float scale, cudaStream_t stream);

@@ -394,6 +394,15 @@ extern "C" int setok_dpc_cluster_pos(const void* feats, int feat_dtype, const fl
   if (pos == nullptr) SETOK_TRY(get_pos_table(h, w, C, &pos, stream));
   SETOK_REQUIRE(aligned16(pos), SETOK_ERR_BAD_ARG, "dpc_cluster: pos table must be 16-byte aligned");
 
+  if (dpc_fused_supported(N, C, k) && (feat_dtype == SETOK_F32 || feat_dtype == SETOK_BF16)) {
+    // N <= 256: one persistent kernel, features read once, distances stay in tensor memory (dpc_fused.cu)
+    SETOK_TRY(launch_dpc_fused(feats, feat_dtype, pos, noise, token_mask, B, N, C, k, threshold, min_cluster_num, x_pos, idx_cluster, score,
+                               index_down, num_clusters, stream));
+    offsets_scan_kernel<<<1, 256, B * sizeof(int32_t), stream>>>(num_clusters, B, offsets);
+    SETOK_LAUNCH_CHECK();
+    return SETOK_OK;
+  }
+
   const long long rows = static_cast<long long>(B) * N;
   int grid = static_cast<int>((rows + 7) / 8);
   if (grid > num_sms() * 16) grid = num_sms() * 16;
