@@ -116,6 +116,13 @@ int setok_vit_forward(const setok_vit* vit, const void* images, int image_dtype,
                       int keep_cls, void* features, int feature_dtype, void* workspace, size_t workspace_bytes,
                       setok_stream_t stream);
 
+/* Same tower, with feature_select('patch') and the position-embedding add of tokenizer.py:164-169 fused into the last
+ * row pass: x_pos (device) f32 [B, N, C] = hidden_states[n_layers_run][:, 1:] + pos_table.  pos_table: (N, C) f32
+ * (device), the PositionalEncoding2D table (module.py:118-146).  Feeds setok_dpc_cluster_embedded / setok_head_forward. */
+int setok_vit_forward_pos(const setok_vit* vit, const void* images, int image_dtype, int B, int n_layers_run,
+                          const float* pos_table, float* x_pos, void* workspace, size_t workspace_bytes,
+                          setok_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * a3+a4: 2-D sincos position embedding add + DPC-kNN clustering.  Replaces PositionalEncoding2D
  * (src/model/setok/module.py:105-146, utils.py:5-10), the add at tokenizer.py:164-169 and
@@ -142,6 +149,14 @@ int setok_dpc_cluster_pos(const void* feats, int feat_dtype, const float* pos_ta
                           int min_cluster_num, float* x_pos, int64_t* idx_cluster, float* score,
                           int64_t* index_down, int32_t* num_clusters, int32_t* offsets, void* workspace,
                           size_t workspace_bytes, setok_stream_t stream);
+
+/* cluster_dpc_knn (tokenizer.py:78-121) on features that already carry the position embedding (the x of
+ * tokenizer.py:168, e.g. from setok_vit_forward_pos): x_pos (device) [B, N, C] f32|bf16 is read once, nothing but the
+ * clustering outputs is written.  Workspace: setok_dpc_workspace_bytes(B, N, C). */
+int setok_dpc_cluster_embedded(const void* x_pos, int dtype, const float* noise, const float* token_mask, int B, int N,
+                               int C, int k, float threshold, int min_cluster_num, int64_t* idx_cluster, float* score,
+                               int64_t* index_down, int32_t* num_clusters, int32_t* offsets, void* workspace,
+                               size_t workspace_bytes, setok_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * a5+a6: group_encoding (tokenizer.py:123-155) + inter_encoder + out (tokenizer.py:179-180) with

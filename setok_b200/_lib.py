@@ -65,7 +65,10 @@ SIGNATURES = {
     "setok_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "setok_vit_workspace_bytes": (c_size_t, [C.POINTER(Vit), c_int]),
     "setok_vit_forward": (c_int, [C.POINTER(Vit), c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    "setok_vit_forward_pos": (c_int, [C.POINTER(Vit), c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "setok_dpc_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "setok_dpc_cluster_embedded": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p,
+                                           c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "setok_dpc_cluster": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "setok_dpc_cluster_pos": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,

@@ -118,9 +118,9 @@ extern "C" size_t setok_vit_workspace_bytes(const setok_vit* vit, int B) {
   return a.off;
 }
 
-extern "C" int setok_vit_forward(const setok_vit* v, const void* images, int image_dtype, int B, int n_layers_run, int keep_cls,
-                                 void* features, int feature_dtype, void* workspace, size_t workspace_bytes, setok_stream_t stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+namespace {
+int vit_forward_impl(const setok_vit* v, const void* images, int image_dtype, int B, int n_layers_run, int keep_cls, void* features,
+                     int feature_dtype, const float* pos_add, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   SETOK_TRY(check_vit(v));
   SETOK_REQUIRE(images && features && B > 0, SETOK_ERR_BAD_ARG, "vit_forward: null images/features or B <= 0");
   SETOK_REQUIRE(n_layers_run >= 0 && n_layers_run <= v->layers, SETOK_ERR_BAD_ARG, "vit_forward: n_layers_run %d outside [0, %d]", n_layers_run, v->layers);
@@ -154,8 +154,22 @@ extern "C" int setok_vit_forward(const setok_vit* v, const void* images, int ima
     SETOK_TRY(launch_gemm(GemmArgs{w.u, F, L.w_fc2, F, w.x, C, SETOK_BF16, L.b_fc2, w.x, C, SETOK_BF16, SETOK_ACT_NONE, R, C, F, nullptr, 0}, stream));
   }
   // feature_select (clip_encoder.py:40-48)
-  SETOK_TRY(launch_select_rows(w.x, features, feature_dtype, B, T, keep_cls ? 0 : 1, C, stream));
+  SETOK_TRY(launch_select_rows(w.x, features, feature_dtype, B, T, keep_cls ? 0 : 1, C, pos_add, stream));
   return SETOK_OK;
+}
+}  // namespace
+
+extern "C" int setok_vit_forward(const setok_vit* v, const void* images, int image_dtype, int B, int n_layers_run, int keep_cls,
+                                 void* features, int feature_dtype, void* workspace, size_t workspace_bytes, setok_stream_t stream) {
+  return vit_forward_impl(v, images, image_dtype, B, n_layers_run, keep_cls, features, feature_dtype, nullptr, workspace, workspace_bytes,
+                          static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int setok_vit_forward_pos(const setok_vit* v, const void* images, int image_dtype, int B, int n_layers_run, const float* pos_table,
+                                     float* x_pos, void* workspace, size_t workspace_bytes, setok_stream_t stream) {
+  SETOK_REQUIRE(pos_table != nullptr && aligned16(pos_table), SETOK_ERR_BAD_ARG, "vit_forward_pos: pos_table must be a 16-byte aligned (N, C) f32 table");
+  return vit_forward_impl(v, images, image_dtype, B, n_layers_run, 0, x_pos, SETOK_F32, pos_table, workspace, workspace_bytes,
+                          static_cast<cudaStream_t>(stream));
 }
 
 // =================================================================================================

@@ -45,9 +45,11 @@ __global__ void __launch_bounds__(256) posadd_sqnorm_kernel(const TI* __restrict
         const float2 a = unpack_bf16x2(u.x), b2 = unpack_bf16x2(u.y);
         v = make_float4(a.x, a.y, b2.x, b2.y);
       }
-      const float4 p = __ldg(reinterpret_cast<const float4*>(pos + static_cast<long long>(t) * C + c));
-      v.x = __fadd_rn(v.x, p.x); v.y = __fadd_rn(v.y, p.y); v.z = __fadd_rn(v.z, p.z); v.w = __fadd_rn(v.w, p.w);
-      *reinterpret_cast<float4*>(x_pos + r * C + c) = v;
+      if (pos != nullptr) {
+        const float4 p = __ldg(reinterpret_cast<const float4*>(pos + static_cast<long long>(t) * C + c));
+        v.x = __fadd_rn(v.x, p.x); v.y = __fadd_rn(v.y, p.y); v.z = __fadd_rn(v.z, p.z); v.w = __fadd_rn(v.w, p.w);
+      }
+      if (x_pos != nullptr) *reinterpret_cast<float4*>(x_pos + r * C + c) = v;
       if (xh != nullptr) {
         // x = hi + lo + O(2^-17 |x|) with hi, lo both bf16: the Gram then runs on the bf16 tensor cores with exact
         // products (hi.hi + hi.lo + lo.hi + lo.lo) and fp32 accumulation
@@ -368,20 +370,22 @@ extern "C" size_t setok_dpc_workspace_bytes(int B, int N, int C) {
   return a.off;
 }
 
-extern "C" int setok_dpc_cluster_pos(const void* feats, int feat_dtype, const float* pos_table, const float* noise,
-                                     const float* token_mask, int B, int h, int w, int C, int k, float threshold,
-                                     int min_cluster_num, float* x_pos, int64_t* idx_cluster, float* score, int64_t* index_down,
-                                     int32_t* num_clusters, int32_t* offsets, void* workspace, size_t workspace_bytes,
-                                     setok_stream_t stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+namespace {
+// embedded: `feats` already carries the position embedding (tokenizer.py:168 done upstream): no table, no x_pos output
+int dpc_cluster_impl(const void* feats, int feat_dtype, const float* pos_table, bool embedded, const float* noise,
+                     const float* token_mask, int B, int h, int w, int C, int k, float threshold,
+                     int min_cluster_num, float* x_pos, int64_t* idx_cluster, float* score, int64_t* index_down,
+                     int32_t* num_clusters, int32_t* offsets, void* workspace, size_t workspace_bytes,
+                     cudaStream_t stream) {
   const int N = h * w;
-  SETOK_REQUIRE(feats && noise && x_pos && idx_cluster && score && index_down && num_clusters && offsets, SETOK_ERR_BAD_ARG, "dpc_cluster: null pointer");
+  SETOK_REQUIRE(feats && noise && (x_pos || embedded) && idx_cluster && score && index_down && num_clusters && offsets, SETOK_ERR_BAD_ARG, "dpc_cluster: null pointer");
   SETOK_REQUIRE(B > 0 && h > 0 && w > 0 && C > 0, SETOK_ERR_BAD_ARG, "dpc_cluster: non-positive shape");
   SETOK_REQUIRE(C % 4 == 0, SETOK_ERR_UNSUPPORTED, "dpc_cluster: C (%d) must be a multiple of 4", C);
   SETOK_REQUIRE(N <= SEL_MAXN, SETOK_ERR_UNSUPPORTED, "dpc_cluster: N (%d) exceeds %d", N, SEL_MAXN);
   SETOK_REQUIRE(k >= 1 && k <= N, SETOK_ERR_BAD_ARG, "dpc_cluster: k (%d) out of range for N=%d (torch.topk would raise)", k, N);
   SETOK_REQUIRE(min_cluster_num >= 1 && min_cluster_num <= N, SETOK_ERR_BAD_ARG, "dpc_cluster: min_cluster_num (%d) out of range for N=%d", min_cluster_num, N);
   SETOK_REQUIRE(aligned16(feats) && aligned16(x_pos), SETOK_ERR_BAD_ARG, "dpc_cluster: feats/x_pos must be 16-byte aligned");
+  SETOK_REQUIRE(feat_dtype == SETOK_F32 || feat_dtype == SETOK_BF16, SETOK_ERR_BAD_ARG, "dpc_cluster: bad feature dtype %d", feat_dtype);
   SETOK_REQUIRE(workspace && workspace_bytes >= setok_dpc_workspace_bytes(B, N, C), SETOK_ERR_WORKSPACE, "dpc_cluster: workspace too small");
   Arena a(workspace, workspace_bytes);
   float* sqn = a.take<float>(static_cast<size_t>(B) * N);
@@ -390,9 +394,10 @@ extern "C" int setok_dpc_cluster_pos(const void* feats, int feat_dtype, const fl
   bf16* xl = a.take<bf16>(static_cast<size_t>(B) * N * C);
   // Gram on the tensor cores when the shapes allow the batched GEMM (leading dimensions multiples of 8 / 4)
   const bool tensor_gram = (C % 8 == 0) && (N % 4 == 0) && g_dpc_tensor_gram;
-  const float* pos = pos_table;
-  if (pos == nullptr) SETOK_TRY(get_pos_table(h, w, C, &pos, stream));
+  const float* pos = embedded ? nullptr : pos_table;
+  if (pos == nullptr && !embedded) SETOK_TRY(get_pos_table(h, w, C, &pos, stream));
   SETOK_REQUIRE(aligned16(pos), SETOK_ERR_BAD_ARG, "dpc_cluster: pos table must be 16-byte aligned");
+  if (embedded) x_pos = nullptr;
 
   if (dpc_fused_supported(N, C, k) && (feat_dtype == SETOK_F32 || feat_dtype == SETOK_BF16)) {
     // N <= 256: one persistent kernel, features read once, distances stay in tensor memory (dpc_fused.cu)
@@ -403,6 +408,9 @@ extern "C" int setok_dpc_cluster_pos(const void* feats, int feat_dtype, const fl
     return SETOK_OK;
   }
 
+  // the fp32-FMA Gram fallback reads fp32 rows: with embedded input those are the features themselves
+  SETOK_REQUIRE(!embedded || tensor_gram || feat_dtype == SETOK_F32, SETOK_ERR_UNSUPPORTED,
+                "dpc_cluster_embedded: bf16 input needs C %% 8 == 0 and N %% 4 == 0 (C=%d N=%d)", C, N);
   const long long rows = static_cast<long long>(B) * N;
   int grid = static_cast<int>((rows + 7) / 8);
   if (grid > num_sms() * 16) grid = num_sms() * 16;
@@ -431,7 +439,7 @@ extern "C" int setok_dpc_cluster_pos(const void* feats, int feat_dtype, const fl
     SETOK_LAUNCH_CHECK();
   } else {
     dim3 ggrid(ceil_div(N, GT), ceil_div(N, GT), B);
-    gram_dist_kernel<<<ggrid, 256, 0, stream>>>(x_pos, sqn, D, N, C, sqrtC);
+    gram_dist_kernel<<<ggrid, 256, 0, stream>>>(embedded ? static_cast<const float*>(feats) : x_pos, sqn, D, N, C, sqrtC);
     SETOK_LAUNCH_CHECK();
   }
 
@@ -443,6 +451,24 @@ extern "C" int setok_dpc_cluster_pos(const void* feats, int feat_dtype, const fl
   offsets_scan_kernel<<<1, 256, B * sizeof(int32_t), stream>>>(num_clusters, B, offsets);
   SETOK_LAUNCH_CHECK();
   return SETOK_OK;
+}
+}  // namespace
+
+extern "C" int setok_dpc_cluster_pos(const void* feats, int feat_dtype, const float* pos_table, const float* noise,
+                                     const float* token_mask, int B, int h, int w, int C, int k, float threshold,
+                                     int min_cluster_num, float* x_pos, int64_t* idx_cluster, float* score, int64_t* index_down,
+                                     int32_t* num_clusters, int32_t* offsets, void* workspace, size_t workspace_bytes,
+                                     setok_stream_t stream) {
+  return dpc_cluster_impl(feats, feat_dtype, pos_table, false, noise, token_mask, B, h, w, C, k, threshold, min_cluster_num, x_pos,
+                          idx_cluster, score, index_down, num_clusters, offsets, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int setok_dpc_cluster_embedded(const void* x_pos_in, int dtype, const float* noise, const float* token_mask, int B, int N, int C,
+                                          int k, float threshold, int min_cluster_num, int64_t* idx_cluster, float* score,
+                                          int64_t* index_down, int32_t* num_clusters, int32_t* offsets, void* workspace,
+                                          size_t workspace_bytes, setok_stream_t stream) {
+  return dpc_cluster_impl(x_pos_in, dtype, nullptr, true, noise, token_mask, B, N, 1, C, k, threshold, min_cluster_num, nullptr,
+                          idx_cluster, score, index_down, num_clusters, offsets, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int setok_dpc_cluster(const void* feats, int feat_dtype, const float* noise, const float* token_mask, int B, int h, int w,

@@ -145,9 +145,11 @@ __global__ void cls_rows_kernel(float* __restrict__ emb, const float* __restrict
   }
 }
 
-// features[b, t', :] = x[b*T + skip + t', :]  (dtype conversion bf16 -> out)
+// features[b, t', :] = x[b*T + skip + t', :] (+ pos[t', :])  (dtype conversion bf16 -> out).  With `pos` the output is
+// the position-embedded tensor of tokenizer.py:168 (feature_select and the add fused in one pass).
 template <class TO>
-__global__ void __launch_bounds__(256) select_rows_kernel(const bf16* __restrict__ x, TO* __restrict__ out, int B, int T, int skip, int C) {
+__global__ void __launch_bounds__(256) select_rows_kernel(const bf16* __restrict__ x, TO* __restrict__ out, int B, int T, int skip, int C,
+                                                          const float* __restrict__ pos) {
   const int To = T - skip;
   const int nvec = C >> 2;
   const long long total = static_cast<long long>(B) * To * nvec;
@@ -157,7 +159,11 @@ __global__ void __launch_bounds__(256) select_rows_kernel(const bf16* __restrict
     const long long r = i / nvec;
     const int t = static_cast<int>(r % To);
     const long long b = r / To;
-    const float4 v = Vec4<bf16>::load(x + ((b * T + skip + t) * C + vi * 4));
+    float4 v = Vec4<bf16>::load(x + ((b * T + skip + t) * C + vi * 4));
+    if (pos != nullptr) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(pos + static_cast<long long>(t) * C + vi * 4));
+      v.x = __fadd_rn(v.x, q.x); v.y = __fadd_rn(v.y, q.y); v.z = __fadd_rn(v.z, q.z); v.w = __fadd_rn(v.w, q.w);
+    }
     Vec4<TO>::store(out + (r * C + vi * 4), v);
   }
 }
@@ -342,11 +348,11 @@ int launch_cls_rows(float* emb, const float* cls, const float* pos, int B, int T
   return SETOK_OK;
 }
 
-int launch_select_rows(const void* x_bf16, void* out, int out_dtype, int B, int T, int skip, int C, cudaStream_t stream) {
+int launch_select_rows(const void* x_bf16, void* out, int out_dtype, int B, int T, int skip, int C, const float* pos, cudaStream_t stream) {
   const long long total = static_cast<long long>(B) * (T - skip) * (C / 4);
   const int grid = grid_for(total, 256, 16);
-  if (out_dtype == SETOK_F32) select_rows_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const bf16*>(x_bf16), static_cast<float*>(out), B, T, skip, C);
-  else if (out_dtype == SETOK_BF16) select_rows_kernel<bf16><<<grid, 256, 0, stream>>>(static_cast<const bf16*>(x_bf16), static_cast<bf16*>(out), B, T, skip, C);
+  if (out_dtype == SETOK_F32) select_rows_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const bf16*>(x_bf16), static_cast<float*>(out), B, T, skip, C, pos);
+  else if (out_dtype == SETOK_BF16) select_rows_kernel<bf16><<<grid, 256, 0, stream>>>(static_cast<const bf16*>(x_bf16), static_cast<bf16*>(out), B, T, skip, C, pos);
   else return fail(SETOK_ERR_BAD_ARG, "select_rows: bad dtype %d", out_dtype);
   SETOK_LAUNCH_CHECK();
   return SETOK_OK;

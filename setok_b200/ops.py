@@ -124,9 +124,11 @@ def attention(qkv: torch.Tensor, heads: int, scale: float, *, seg_off: Optional[
 
 
 def dpc_cluster(feats: torch.Tensor, noise: torch.Tensor, hw: Tuple[int, int], k: int, threshold: float, min_cluster_num: int,
-                pos_table: Optional[torch.Tensor] = None, token_mask: Optional[torch.Tensor] = None):
+                pos_table: Optional[torch.Tensor] = None, token_mask: Optional[torch.Tensor] = None, embedded: bool = False):
     """feats (B, N, C) f32|bf16, noise (B, N) f32.  Returns x_pos (B,N,C) f32, idx_cluster (B,N) i64, score (B,N) f32,
-    index_down (B,N) i64 (-1 padded), num_clusters (B,) i32, offsets (B+1,) i32 — all on the device, no sync."""
+    index_down (B,N) i64 (-1 padded), num_clusters (B,) i32, offsets (B+1,) i32 — all on the device, no sync.
+    embedded=True: `feats` already carries the position embedding (tokenizer.py:168); it is read once and returned
+    as x_pos unchanged (no table, no copy)."""
     dev = _dev(feats, noise, pos_table, token_mask)
     B, N, Cc = feats.shape
     h, w = hw
@@ -138,7 +140,7 @@ def dpc_cluster(feats: torch.Tensor, noise: torch.Tensor, hw: Tuple[int, int], k
         raise SetokError("pos_table must be float32 with N*C elements")
     if token_mask is not None:
         token_mask = token_mask.to(torch.float32).contiguous()
-    x_pos = torch.empty(B, N, Cc, dtype=torch.float32, device=dev)
+    x_pos = feats if embedded else torch.empty(B, N, Cc, dtype=torch.float32, device=dev)
     idx = torch.empty(B, N, dtype=torch.int64, device=dev)
     score = torch.empty(B, N, dtype=torch.float32, device=dev)
     down = torch.empty(B, N, dtype=torch.int64, device=dev)
@@ -148,8 +150,13 @@ def dpc_cluster(feats: torch.Tensor, noise: torch.Tensor, hw: Tuple[int, int], k
     nbytes = lib.setok_dpc_workspace_bytes(B, N, Cc)
     ws = workspace(dev, nbytes, "dpc")
     with torch.cuda.device(dev):
-        st = lib.setok_dpc_cluster_pos(feats.data_ptr(), _dt(feats), _p(pos_table), noise.data_ptr(), _p(token_mask), B, h, w, Cc, k,
-                                       float(threshold), min_cluster_num, x_pos.data_ptr(), idx.data_ptr(), score.data_ptr(),
-                                       down.data_ptr(), numc.data_ptr(), offs.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev))
+        if embedded:
+            st = lib.setok_dpc_cluster_embedded(feats.data_ptr(), _dt(feats), noise.data_ptr(), _p(token_mask), B, N, Cc, k, float(threshold),
+                                                min_cluster_num, idx.data_ptr(), score.data_ptr(), down.data_ptr(), numc.data_ptr(),
+                                                offs.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev))
+        else:
+            st = lib.setok_dpc_cluster_pos(feats.data_ptr(), _dt(feats), _p(pos_table), noise.data_ptr(), _p(token_mask), B, h, w, Cc, k,
+                                           float(threshold), min_cluster_num, x_pos.data_ptr(), idx.data_ptr(), score.data_ptr(),
+                                           down.data_ptr(), numc.data_ptr(), offs.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev))
     check(st, "setok_dpc_cluster")
     return x_pos, idx, score, down, numc, offs

@@ -259,11 +259,14 @@ class CLIPVisionTower(nn.Module):
         return idx
 
     @torch.no_grad()
-    def forward(self, images, interpolate_pos_encoding: bool = False):
+    def forward(self, images, interpolate_pos_encoding: bool = False, pos_embedding=None):
+        """clip_encoder.py:50-62.  ``pos_embedding`` (a PositionalEncoding2D, 'patch' features only): the position-embedding
+        add of tokenizer.py:164-169 is fused into the tower's last row pass and the result is the float32 tensor
+        ``features + pos`` (what tokenizer.py:168 calls x) instead of the features."""
         if self.select_feature not in ("patch", "cls_patch"):
             raise ValueError(f"Unexpected select feature: {self.select_feature}")
         if type(images) is list:       # clip_encoder.py:52-57: per-image loop -> list of (1, N, C)
-            return [self.forward(im.unsqueeze(0), interpolate_pos_encoding) for im in images]
+            return [self.forward(im.unsqueeze(0), interpolate_pos_encoding, pos_embedding) for im in images]
         if not self.is_loaded:
             raise SetokError("vision tower not loaded: call load_model() first")
         vit, _, _ = self._packed or self._pack()
@@ -284,10 +287,21 @@ class CLIPVisionTower(nn.Module):
         keep_cls = 1 if self.select_feature == "cls_patch" else 0
         N = (vit.image_size // vit.patch) ** 2 + keep_cls
         feat_dtype = torch.bfloat16 if x.dtype == torch.bfloat16 else torch.float32
-        feats = torch.empty(B, N, vit.hidden, dtype=feat_dtype, device=dev)
         lib = _lib.load()
         nbytes = lib.setok_vit_workspace_bytes(C.byref(vit), B)
         ws = ops.workspace(dev, nbytes, "vit")
+        if pos_embedding is not None:
+            if keep_cls:
+                raise SetokError("the fused position-embedding add needs mm_vision_select_feature='patch'")
+            g = vit.image_size // vit.patch
+            pos = pos_embedding.table(g, g, dev)
+            x_pos = torch.empty(B, N, vit.hidden, dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                st = lib.setok_vit_forward_pos(C.byref(vit), x.data_ptr(), ops._dt(x), B, self.layers_to_run(), pos.data_ptr(),
+                                               x_pos.data_ptr(), ws.data_ptr(), ws.numel(), ops._stream(dev))
+            _lib.check(st, "setok_vit_forward_pos")
+            return x_pos
+        feats = torch.empty(B, N, vit.hidden, dtype=feat_dtype, device=dev)
         with torch.cuda.device(dev):
             st = lib.setok_vit_forward(C.byref(vit), x.data_ptr(), ops._dt(x), B, self.layers_to_run(), keep_cls, feats.data_ptr(),
                                        ops._dt(feats), ws.data_ptr(), ws.numel(), ops._stream(dev))
@@ -442,9 +456,10 @@ class SetokTokenizer(nn.Module):
     # -- forward -----------------------------------------------------------------------------
     @torch.no_grad()
     def encode_features(self, feats: torch.Tensor, k=None, threshold=None, token_mask=None, noise: Optional[torch.Tensor] = None,
-                        token_dtype=None, return_group_features: bool = False):
+                        token_dtype=None, return_group_features: bool = False, embedded: bool = False):
         """The head of tokenizer.py:162-182 for a batch of tower features (B, N, C).  Returns
-        (RaggedTokens, idx_cluster (B, N) int64, score (B, 1, N))."""
+        (RaggedTokens, idx_cluster (B, N) int64, score (B, 1, N)).  ``embedded``: `feats` is already
+        ``features + pos`` in float32 (``image_feature_encoder(images, pos_embedding=...)``)."""
         head, _ = self._packed_head or self._pack()
         dev = self.device
         if feats.dim() == 2:
@@ -467,9 +482,15 @@ class SetokTokenizer(nn.Module):
             noise = noise.to(device=dev, dtype=torch.float32).reshape(B, N).contiguous()
         if token_mask is not None:
             token_mask = token_mask.to(dev).reshape(B, N)
-        pos = self.position_embedding.table(h, w, dev)
-        x_pos, idx, score, down, numc, offs = ops.dpc_cluster(feats, noise, (h, w), int(_k), float(_threshold), int(self.min_cluster_num),
-                                                              pos_table=pos, token_mask=token_mask)
+        if embedded:
+            if feats.dtype != torch.float32:
+                raise SetokError("embedded features must be float32 (the head's residual stream starts from them)")
+            x_pos, idx, score, down, numc, offs = ops.dpc_cluster(feats, noise, (h, w), int(_k), float(_threshold), int(self.min_cluster_num),
+                                                                  token_mask=token_mask, embedded=True)
+        else:
+            pos = self.position_embedding.table(h, w, dev)
+            x_pos, idx, score, down, numc, offs = ops.dpc_cluster(feats, noise, (h, w), int(_k), float(_threshold), int(self.min_cluster_num),
+                                                                  pos_table=pos, token_mask=token_mask)
         token_dtype = token_dtype or (torch.bfloat16 if feats.dtype == torch.bfloat16 else torch.float32)
         tokens = torch.empty(B * N, self.token_feat_dim, dtype=token_dtype, device=dev)
         gf = torch.empty(B * N, Cc, dtype=torch.float32, device=dev) if return_group_features else None
@@ -502,7 +523,14 @@ class SetokTokenizer(nn.Module):
             x = torch.stack(list(x), dim=0)
             if isinstance(noise, (list, tuple)):
                 noise = torch.stack(list(noise), dim=0)
-        feats = self.image_feature_encoder(x, interpolate_pos_encoding)
+        tower = self.image_feature_encoder
+        if tower.select_feature == "patch" and torch.is_tensor(x):
+            # a1..a3 in one call: the tower's last row pass drops CLS and adds the position embedding (tokenizer.py:164-169)
+            x_pos = tower(x, interpolate_pos_encoding, pos_embedding=self.position_embedding)
+            token_dtype = torch.bfloat16 if x.dtype == torch.bfloat16 else torch.float32
+            return self.encode_features(x_pos, k=k, threshold=threshold, token_mask=token_mask, noise=noise, token_dtype=token_dtype,
+                                        embedded=True)
+        feats = tower(x, interpolate_pos_encoding)
         return self.encode_features(feats, k=k, threshold=threshold, token_mask=token_mask, noise=noise)
 
     def _forward_mixed(self, images, k, threshold, noise, interpolate_pos_encoding):

@@ -94,6 +94,30 @@ def test_tower_vs_oracle(C, heads, L, patch, img, B):
         assert gotb.dtype == torch.bfloat16 and _err(gotb, ref)[1] < 1.5e-2
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_forward_fused_pos_add_equals_two_step_path(dtype):
+    """SetokTokenizer.forward fuses feature_select + the position-embedding add into the tower's last row pass and
+    clusters the embedded tensor in place (setok_vit_forward_pos -> setok_dpc_cluster_embedded).  It must agree bit for
+    bit with the two public steps tower(images) -> encode_features(feats) (clip_encoder.py:50-62, tokenizer.py:162-182)."""
+    C, L, H, P, IMG, B = 128, 2, 2, 4, 64, 5            # N = 256
+    cfg = dict(hidden_size=C, intermediate_size=4 * C, num_hidden_layers=L, num_attention_heads=H, image_size=IMG, patch_size=P)
+    tok = _make_tokenizer(C, 64, 256, 8, 0.5, cfg, seed=3)
+    images = torch.randn(B, 3, IMG, IMG, generator=torch.Generator().manual_seed(5)).to(DEV).to(dtype)
+    N = (IMG // P) ** 2
+    noise = torch.rand(B, N, generator=torch.Generator().manual_seed(6)).to(DEV)
+    rt, idx, score = tok(images, k=8, noise=noise)
+    feats = tok.image_feature_encoder(images)
+    assert feats.dtype == dtype
+    rt2, idx2, score2 = tok.encode_features(feats, k=8, noise=noise)
+    x_pos = tok.image_feature_encoder(images, pos_embedding=tok.position_embedding)
+    pos = tok.position_embedding.table(IMG // P, IMG // P, DEV).reshape(1, N, C)
+    assert x_pos.dtype == torch.float32 and torch.equal(x_pos, feats.float() + pos)
+    assert torch.equal(idx, idx2) and torch.equal(score, score2)
+    assert torch.equal(rt.offsets, rt2.offsets) and rt.data.dtype == rt2.data.dtype
+    n = int(rt.offsets[-1])
+    assert torch.equal(rt.data[:n], rt2.data[:n])
+
+
 def test_head_golden():
     """Head golden (C=64): clustering bit-exact, group features and tokens within bf16-GEMM tolerance."""
     g = load_golden("head")
