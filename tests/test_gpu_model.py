@@ -118,6 +118,25 @@ def test_forward_fused_pos_add_equals_two_step_path(dtype):
     assert torch.equal(rt.data[:n], rt2.data[:n])
 
 
+def test_stream_tokenize_matches_direct_forward():
+    """The host<->device streaming API (pinned H2D on a copy stream, read-back on its own stream) returns, batch by
+    batch and in order, exactly what a direct forward returns."""
+    from setok_b200.pipeline import stream_tokenize
+    C, L, H, P, IMG, B = 128, 2, 2, 4, 32, 4
+    cfg = dict(hidden_size=C, intermediate_size=4 * C, num_hidden_layers=L, num_attention_heads=H, image_size=IMG, patch_size=P)
+    tok = _make_tokenizer(C, 64, 256, 8, 0.5, cfg, seed=4)
+    N = (IMG // P) ** 2
+    g = torch.Generator().manual_seed(9)
+    batches = [(torch.randn(B, 3, IMG, IMG, generator=g).pin_memory(), torch.rand(B, N, generator=g).pin_memory()) for _ in range(4)]
+    got = list(stream_tokenize(tok, iter(batches), k=8))
+    assert len(got) == len(batches)
+    for (imgs, noise), res in zip(batches, got):
+        rt, idx, score = tok(imgs.to(DEV), k=8, noise=noise.to(DEV))
+        n = int(rt.offsets[-1])
+        assert torch.equal(res.offsets, rt.offsets.cpu()) and torch.equal(res.idx_cluster, idx.cpu())
+        assert torch.equal(res.score, score.cpu()) and torch.equal(res.tokens, rt.data[:n].cpu())
+
+
 def test_head_golden():
     """Head golden (C=64): clustering bit-exact, group features and tokens within bf16-GEMM tolerance."""
     g = load_golden("head")
