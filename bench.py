@@ -42,7 +42,7 @@ KNN_K = 16
 BATCH = 256
 # dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch, mean of fc2/qkv/out_proj/fc1 (profiles/r01_ncu_summary.md)
 NCU_GEMM_DRAM_BYTES_PER_LAUNCH = (804.5e6 + 494.0e6 + 363.0e6 + 631.8e6) / 4
-NCU_CLUSTER_DRAM_BYTES_PER_LAUNCH = (269.5e6 + 221.7e6) + (269.4e6 + 51.0e6) + (67.5e6 + 1.5e6)   # posadd + gram + select
+NCU_CLUSTER_DRAM_BYTES_PER_LAUNCH = 269.0e6 + 7.5e6   # dpc_fused_kernel, dram read + write (profiles/r01_ncu_summary.md)
 
 
 def peaks():
@@ -371,7 +371,9 @@ def run_ours(args):
         "roofline_cluster": {"kernel": "dpc_fused_kernel (a4 on the position-embedded tensor; a3 is fused into the tower's last row pass), B=256 N=256 C=1024 feature-injected", "bound": "hbm",
                              "achieved": cl_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": cl_gbs / pk["hbm"], "traffic": NCU_CLUSTER_DRAM_BYTES_PER_LAUNCH,
                              "bytes_per_launch": cl_bytes, "ms_per_launch": cl_ms, "with_pos_ms": cl_ms_pos, "k_min_mean_max": kstats,
-                             "tensor_frac_if_compute": (BATCH * 2.0 * 256 * 256 * 1024 / (cl_ms * 1e-3) / 1e12) / pk["tf_burst"]},
+                             "tensor_frac_if_compute": (BATCH * 2.0 * 256 * 256 * 1024 / (cl_ms * 1e-3) / 1e12) / pk["tf_burst"],
+                             "tensor_frac_executed": (4 * BATCH * 2.0 * 256 * 256 * 1024 / (cl_ms * 1e-3) / 1e12) / pk["tf_burst"],
+                             "note": "the Gram runs as an exact 4-term bf16 hi/lo split on tcgen05 (4x the algorithmic FLOPs); the 256x256 fp32 distance matrix fills TMEM, so the MMA phase (48 us/image) and the select phase (21 us/image) serialise; 256 images = 2 waves on 148 SMs"},
     }
     if world == 1 and not args.no_cpu:
         n = args.cpu_sample

@@ -12,6 +12,7 @@ feats = mog_features(256, 256, 1024, 7, dev)
 if os.environ.get("SETOK_DPC_BF16"):
     feats = feats.to(torch.bfloat16)
 noise = torch.rand(256, 256, device=dev)
+emb = bool(os.environ.get("SETOK_DPC_EMBEDDED"))
 for _ in range(4):
-    ops.dpc_cluster(feats, noise, (16, 16), int(os.environ.get("SETOK_DPC_K", "16")), 0.5, 64)
+    ops.dpc_cluster(feats, noise, (16, 16), int(os.environ.get("SETOK_DPC_K", "16")), 0.5, 64, embedded=emb)
 torch.cuda.synchronize()
