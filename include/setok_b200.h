@@ -204,6 +204,48 @@ int setok_project(const setok_projector* proj, const void* tokens, int token_dty
                   const int32_t* m_dev, void* out, int out_dtype, void* workspace, size_t workspace_bytes,
                   setok_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * a10: SetokDeTokenizer.forward (src/model/setok/detokenizer.py:101-120) as a consumer of the ragged
+ * token batch: mapper_fc_in -> Q-Former (module.py:476-583; learned queries cross-attend the image's K_b tokens every
+ * cross_attention_freq layers, text FFN deleted detokenizer.py:94-96) -> decoder_fc_in -> + PositionalEncoding2D ->
+ * decoder_depth timm ViT blocks -> decoder_norm.  The reference's padded (B, K_max, C_tok) + attention_masks pair is
+ * replaced by packed rows + offsets (varlen cross-attention, no -10000 padding mask); the missing `return` is added.
+ */
+typedef struct {
+  const void* w_qkv; const float* b_qkv;     /* attention.self.{query,key,value} fused: bf16 [3H, H] */
+  const void* w_so; const float* b_so;       /* attention.output.dense bf16 [H, H] */
+  const float* ln_s_g; const float* ln_s_b;  /* attention.output.LayerNorm */
+  int has_cross;                             /* layer_num % cross_attention_freq == 0 (module.py:484-493) */
+  const void* w_cq; const float* b_cq;       /* crossattention.self.query bf16 [H, H] */
+  const void* w_ckv; const float* b_ckv;     /* crossattention.self.{key,value} fused: bf16 [2H, H] (encoder_width = H) */
+  const void* w_co; const float* b_co;       /* crossattention.output.dense */
+  const float* ln_c_g; const float* ln_c_b;  /* crossattention.output.LayerNorm */
+  const void* w_f1; const float* b_f1;       /* intermediate_query.dense bf16 [I, H], GELU(erf) */
+  const void* w_f2; const float* b_f2;       /* output_query.dense bf16 [H, I] */
+  const float* ln_f_g; const float* ln_f_b;  /* output_query.LayerNorm */
+} setok_qformer_layer;
+
+typedef struct {
+  int token_dim, hidden, q_heads, q_inter, q_layers, grid;      /* n_queries = grid * grid */
+  int dec_dim, dec_heads, dec_mlp, dec_depth;
+  float q_ln_eps, dec_ln_eps;                                   /* 1e-12 (BertConfig), 1e-5 (nn.LayerNorm) */
+  const void* w_map_in; const float* b_map_in;                  /* mapper_fc_in bf16 [H, C_tok] */
+  const float* mask_tokens;                                     /* f32 [Q, H] */
+  const float* emb_ln_g; const float* emb_ln_b;                 /* mapper.embeddings.LayerNorm */
+  const setok_qformer_layer* qlayer;                            /* host array [q_layers] */
+  const void* w_dec_in; const float* b_dec_in;                  /* decoder_fc_in bf16 [Dd, H] */
+  const float* pos;                                             /* f32 [Q, Dd]: PositionalEncoding2D(hidden)(grid, grid)[..., :Dd] */
+  const setok_vit_layer* block;                                 /* host array [dec_depth]: timm Block (w_o = attn.proj) */
+  const float* norm_g; const float* norm_b;                     /* decoder_norm */
+} setok_detok;
+
+size_t setok_detok_workspace_bytes(const setok_detok* detok, int B, int rows_capacity);
+/* tokens (device) [rows_capacity, C_tok] f32|bf16, rows [offsets[b], offsets[b+1]) = image b's tokens; offsets (device)
+ * int32 [B+1].  out (device) [B, grid*grid, dec_dim] f32|bf16. */
+int setok_detok_forward(const setok_detok* detok, const void* tokens, int token_dtype, const int32_t* offsets, int B,
+                        int rows_capacity, void* out, int out_dtype, void* workspace, size_t workspace_bytes,
+                        setok_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

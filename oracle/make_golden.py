@@ -236,6 +236,82 @@ def golden_projectors(ns):
     _save("projectors", **out)
 
 
+DETOK_DIMS = dict(token_dim=48, hidden=64, q_heads=4, q_inter=128, q_layers=3, cross_freq=2, grid=4, dec_dim=64, dec_depth=2, dec_mlp=256)
+DETOK_DEC_HEADS = 4
+DETOK_K = [5, 2, 7]
+
+
+def golden_detok(ns):
+    """SetokDeTokenizer.forward (detokenizer.py:101-120) composed from the reference's own BertEmbeddings / BertEncoder /
+    PositionalEncoding2D classes (executed unmodified) and HF ViTLayer standing in for timm's Block (same pre-LN block;
+    timm is not installed).  `SetokDeTokenizer.__init__` itself cannot run here: it needs timm, diffusers and a local
+    bert-base-uncased config; BertModel.__init__ does not construct under transformers 5.x (see oracle/detok_oracle.py)."""
+    import torch.nn.functional as F
+    from transformers.models.bert import BertConfig
+    from transformers.models.vit.configuration_vit import ViTConfig
+    from transformers.models.vit.modeling_vit import ViTLayer
+    from oracle import detok_oracle as D
+    M = ns.module
+    d = DETOK_DIMS
+    p = D.make_detok_params(**d, seed=11)
+    Q = d["grid"] ** 2
+    cfg = BertConfig()                               # == bert-base-uncased's config.json (detokenizer.py:80)
+    cfg.hidden_size, cfg.num_attention_heads, cfg.intermediate_size = d["hidden"], d["q_heads"], d["q_inter"]
+    cfg.encoder_width, cfg.add_cross_attention, cfg.cross_attention_freq = d["hidden"], True, d["cross_freq"]   # :82-86
+    cfg.query_length, cfg.num_hidden_layers = Q, d["q_layers"]                                                  # :87-88
+    emb, enc = M.BertEmbeddings(cfg).eval(), M.BertEncoder(cfg).eval()
+    for layer in enc.layer:                                                                                     # :94-96
+        layer.output = None
+        layer.intermediate = None
+    emb.load_state_dict({k[len("mapper.embeddings."):]: v for k, v in p.items() if k.startswith("mapper.embeddings.")}, strict=False)
+    missing, unexpected = enc.load_state_dict({k[len("mapper.encoder."):]: v for k, v in p.items() if k.startswith("mapper.encoder.")}, strict=False)
+    assert not unexpected and not missing, (missing, unexpected)
+    pe = M.PositionalEncoding2D(d["hidden"])
+
+    g = torch.Generator().manual_seed(12)
+    tokens = torch.randn(sum(DETOK_K), d["token_dim"], generator=g)
+    offsets = [0]
+    for k_ in DETOK_K:
+        offsets.append(offsets[-1] + k_)
+    x, mask = D.pad_ragged(tokens, offsets)
+    B = x.shape[0]
+    with torch.no_grad():
+        enc_in = F.linear(x, p["mapper_fc_in.weight"], p["mapper_fc_in.bias"])                                  # :104
+        h0 = emb(query_embeds=p["mask_tokens"].expand(B, -1, -1))
+        ext = torch.zeros(B, 1, 1, Q)                                               # get_extended_attention_mask(ones)
+        inv = (1.0 - mask[:, None, None, :]) * torch.finfo(torch.float32).min       # invert_attention_mask
+        h = enc(h0, attention_mask=ext, head_mask=[None] * d["q_layers"], encoder_hidden_states=enc_in, encoder_attention_mask=inv,
+                query_length=Q, return_dict=True).last_hidden_state                                             # :105-109
+        y = F.linear(h, p["decoder_fc_in.weight"], p["decoder_fc_in.bias"])                                     # :111
+        pos = pe(y.reshape(B, d["grid"], d["grid"], -1)).reshape(B, Q, -1)                                      # :112-114
+        y = y + pos
+        vcfg = ViTConfig(hidden_size=d["dec_dim"], num_attention_heads=DETOK_DEC_HEADS, intermediate_size=d["dec_mlp"], hidden_act="gelu",
+                         layer_norm_eps=1e-5, qkv_bias=True, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+        vcfg._attn_implementation = "eager"
+        C = d["dec_dim"]
+        for i in range(d["dec_depth"]):
+            blk = ViTLayer(vcfg).eval()
+            b = f"pixel_decoder.{i}."
+            sd = {"layernorm_before.weight": p[b + "norm1.weight"], "layernorm_before.bias": p[b + "norm1.bias"],
+                  "layernorm_after.weight": p[b + "norm2.weight"], "layernorm_after.bias": p[b + "norm2.bias"],
+                  "attention.output.dense.weight": p[b + "attn.proj.weight"], "attention.output.dense.bias": p[b + "attn.proj.bias"],
+                  "intermediate.dense.weight": p[b + "mlp.fc1.weight"], "intermediate.dense.bias": p[b + "mlp.fc1.bias"],
+                  "output.dense.weight": p[b + "mlp.fc2.weight"], "output.dense.bias": p[b + "mlp.fc2.bias"]}
+            for j, n in enumerate(("query", "key", "value")):
+                sd[f"attention.attention.{n}.weight"] = p[b + "attn.qkv.weight"][j * C:(j + 1) * C]
+                sd[f"attention.attention.{n}.bias"] = p[b + "attn.qkv.bias"][j * C:(j + 1) * C]
+            missing, unexpected = blk.load_state_dict(sd, strict=False)
+            assert not unexpected and not missing, (missing, unexpected)
+            o = blk(y)
+            y = o[0] if isinstance(o, tuple) else o
+        out = F.layer_norm(y, (C,), p["decoder_norm.weight"], p["decoder_norm.bias"], 1e-5)                     # :120
+    keys = sorted(p.keys())
+    save = {f"param/{k}": p[k] for k in keys}
+    save.update(dict(keys=np.array(keys), tokens=tokens, offsets=np.array(offsets, dtype=np.int32), x=x, mask=mask, qformer=h, pos=pos[0], out=out,
+                     dims=np.array([d[k] for k in ("token_dim", "hidden", "q_heads", "q_inter", "q_layers", "cross_freq", "grid", "dec_dim", "dec_depth", "dec_mlp")] + [DETOK_DEC_HEADS])))
+    _save("detok", **save)
+
+
 def main():
     if not ref_loader.available():
         raise SystemExit("reference tree not present: goldens can only be generated in the build container")
@@ -246,6 +322,7 @@ def main():
     golden_block_and_head(ns)
     golden_tower_and_e2e(ns)
     golden_projectors(ns)
+    golden_detok(ns)
 
 
 if __name__ == "__main__":

@@ -6,6 +6,7 @@ from ._lib import SetokError  # noqa: F401
 from .builder import build_vision_projector, build_vision_tower, encode_images  # noqa: F401
 from .ragged import RaggedTokens  # noqa: F401
 from .tokenizer import CLIPVisionTower, SetokTokenizer  # noqa: F401
+from .detokenizer import SetokDeTokenizer  # noqa: F401
 
-__all__ = ["SetokTokenizer", "CLIPVisionTower", "RaggedTokens", "build_vision_tower", "build_vision_projector",
+__all__ = ["SetokTokenizer", "SetokDeTokenizer", "CLIPVisionTower", "RaggedTokens", "build_vision_tower", "build_vision_projector",
            "encode_images", "SetokError"]

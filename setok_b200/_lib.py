@@ -51,6 +51,21 @@ class Projector(C.Structure):
                 ("norm_g", c_void_p), ("norm_b", c_void_p)]
 
 
+class QFormerLayer(C.Structure):
+    _fields_ = [("w_qkv", c_void_p), ("b_qkv", c_void_p), ("w_so", c_void_p), ("b_so", c_void_p), ("ln_s_g", c_void_p), ("ln_s_b", c_void_p),
+                ("has_cross", c_int), ("w_cq", c_void_p), ("b_cq", c_void_p), ("w_ckv", c_void_p), ("b_ckv", c_void_p), ("w_co", c_void_p),
+                ("b_co", c_void_p), ("ln_c_g", c_void_p), ("ln_c_b", c_void_p), ("w_f1", c_void_p), ("b_f1", c_void_p), ("w_f2", c_void_p),
+                ("b_f2", c_void_p), ("ln_f_g", c_void_p), ("ln_f_b", c_void_p)]
+
+
+class Detok(C.Structure):
+    _fields_ = [("token_dim", c_int), ("hidden", c_int), ("q_heads", c_int), ("q_inter", c_int), ("q_layers", c_int), ("grid", c_int),
+                ("dec_dim", c_int), ("dec_heads", c_int), ("dec_mlp", c_int), ("dec_depth", c_int), ("q_ln_eps", c_float), ("dec_ln_eps", c_float),
+                ("w_map_in", c_void_p), ("b_map_in", c_void_p), ("mask_tokens", c_void_p), ("emb_ln_g", c_void_p), ("emb_ln_b", c_void_p),
+                ("qlayer", C.POINTER(QFormerLayer)), ("w_dec_in", c_void_p), ("b_dec_in", c_void_p), ("pos", c_void_p),
+                ("block", C.POINTER(VitLayer)), ("norm_g", c_void_p), ("norm_b", c_void_p)]
+
+
 # name -> (restype, argtypes); every symbol include/setok_b200.h declares
 SIGNATURES = {
     "setok_last_error": (C.c_char_p, []),
@@ -76,6 +91,8 @@ SIGNATURES = {
     "setok_head_workspace_bytes": (c_size_t, [C.POINTER(Head), c_int, c_int]),
     "setok_head_forward": (c_int, [C.POINTER(Head), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
                                    c_void_p, c_void_p, c_size_t, c_void_p]),
+    "setok_detok_workspace_bytes": (c_size_t, [C.POINTER(Detok), c_int, c_int]),
+    "setok_detok_forward": (c_int, [C.POINTER(Detok), c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "setok_project_workspace_bytes": (c_size_t, [C.POINTER(Projector), c_int]),
     "setok_project": (c_int, [C.POINTER(Projector), c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
 }

@@ -39,6 +39,21 @@ int check_vit(const setok_vit* v) {
   return SETOK_OK;
 }
 
+// One pre-LN transformer layer on the bf16 residual stream x [R, C] of sequences of T rows:
+//   x += W_o MHSA(LN1(x)); x += W_2 act(W_1 LN2(x))      (CLIPEncoderLayer, modeling_clip.py:363-386; timm Block)
+int run_preln_layer(const setok_vit_layer& L, bf16* x, bf16* h, bf16* qkv, bf16* ao, bf16* u, int R, int T, int C, int F, int heads,
+                    float eps, int act, cudaStream_t stream) {
+  const float scale = 1.0f / std::sqrt(static_cast<float>(C / heads));
+  SETOK_TRY(launch_layernorm(x, SETOK_BF16, h, SETOK_BF16, L.ln1_g, L.ln1_b, eps, R, C, nullptr, nullptr, stream));
+  SETOK_TRY(launch_gemm(GemmArgs{h, C, L.w_qkv, C, qkv, 3LL * C, SETOK_BF16, L.b_qkv, nullptr, 0, 0, SETOK_ACT_NONE, R, 3 * C, C, nullptr, 0}, stream));
+  SETOK_TRY(launch_attention(qkv, ao, R, C, heads, scale, nullptr, nullptr, T, nullptr, stream));
+  SETOK_TRY(launch_gemm(GemmArgs{ao, C, L.w_o, C, x, C, SETOK_BF16, L.b_o, x, C, SETOK_BF16, SETOK_ACT_NONE, R, C, C, nullptr, 0}, stream));
+  SETOK_TRY(launch_layernorm(x, SETOK_BF16, h, SETOK_BF16, L.ln2_g, L.ln2_b, eps, R, C, nullptr, nullptr, stream));
+  SETOK_TRY(launch_gemm(GemmArgs{h, C, L.w_fc1, C, u, F, SETOK_BF16, L.b_fc1, nullptr, 0, 0, act, R, F, C, nullptr, 0}, stream));
+  SETOK_TRY(launch_gemm(GemmArgs{u, F, L.w_fc2, F, x, C, SETOK_BF16, L.b_fc2, x, C, SETOK_BF16, SETOK_ACT_NONE, R, C, F, nullptr, 0}, stream));
+  return SETOK_OK;
+}
+
 struct BlockBufs { bf16 *h, *qkv, *ao, *u; float* S; bf16* P; };
 
 // Block.forward (reference module.py:95-100): depth x [x += Attn_i(norm1(x))], then x += Mlp(norm2(x)).
@@ -139,19 +154,11 @@ int vit_forward_impl(const setok_vit* v, const void* images, int image_dtype, in
   SETOK_TRY(launch_cls_rows(w.emb, v->cls, v->pos, B, T, C, stream));
   SETOK_TRY(launch_layernorm(w.emb, SETOK_F32, w.x, SETOK_BF16, v->pre_ln_g, v->pre_ln_b, v->ln_eps, R, C, nullptr, nullptr, stream));
 
-  const float scale = 1.0f / std::sqrt(static_cast<float>(C / v->heads));
   for (int l = 0; l < n_layers_run; ++l) {
     const setok_vit_layer& L = v->layer[l];
     SETOK_REQUIRE(L.w_qkv && L.b_qkv && L.w_o && L.b_o && L.w_fc1 && L.b_fc1 && L.w_fc2 && L.b_fc2 && L.ln1_g && L.ln1_b && L.ln2_g && L.ln2_b,
                   SETOK_ERR_BAD_ARG, "vit_forward: null weights in layer %d", l);
-    // CLIPEncoderLayer.forward (modeling_clip.py:363-386)
-    SETOK_TRY(launch_layernorm(w.x, SETOK_BF16, w.h, SETOK_BF16, L.ln1_g, L.ln1_b, v->ln_eps, R, C, nullptr, nullptr, stream));
-    SETOK_TRY(launch_gemm(GemmArgs{w.h, C, L.w_qkv, C, w.qkv, 3LL * C, SETOK_BF16, L.b_qkv, nullptr, 0, 0, SETOK_ACT_NONE, R, 3 * C, C, nullptr, 0}, stream));
-    SETOK_TRY(launch_attention(w.qkv, w.ao, R, C, v->heads, scale, nullptr, nullptr, T, nullptr, stream));
-    SETOK_TRY(launch_gemm(GemmArgs{w.ao, C, L.w_o, C, w.x, C, SETOK_BF16, L.b_o, w.x, C, SETOK_BF16, SETOK_ACT_NONE, R, C, C, nullptr, 0}, stream));
-    SETOK_TRY(launch_layernorm(w.x, SETOK_BF16, w.h, SETOK_BF16, L.ln2_g, L.ln2_b, v->ln_eps, R, C, nullptr, nullptr, stream));
-    SETOK_TRY(launch_gemm(GemmArgs{w.h, C, L.w_fc1, C, w.u, F, SETOK_BF16, L.b_fc1, nullptr, 0, 0, SETOK_ACT_QUICK_GELU, R, F, C, nullptr, 0}, stream));
-    SETOK_TRY(launch_gemm(GemmArgs{w.u, F, L.w_fc2, F, w.x, C, SETOK_BF16, L.b_fc2, w.x, C, SETOK_BF16, SETOK_ACT_NONE, R, C, F, nullptr, 0}, stream));
+    SETOK_TRY(run_preln_layer(L, w.x, w.h, w.qkv, w.ao, w.u, R, T, C, F, v->heads, v->ln_eps, SETOK_ACT_QUICK_GELU, stream));
   }
   // feature_select (clip_encoder.py:40-48)
   SETOK_TRY(launch_select_rows(w.x, features, feature_dtype, B, T, keep_cls ? 0 : 1, C, pos_add, stream));
@@ -274,5 +281,109 @@ extern "C" int setok_project(const setok_projector* p, const void* tokens, int t
       cur = dst;
     }
   }
+  return SETOK_OK;
+}
+
+// =================================================================================================
+namespace {
+struct DetokBufs { bf16 *tokb, *enc, *kv, *h, *a, *q, *qkv, *ctx, *u, *x, *hx; float* t32; int32_t* idx; };
+
+void detok_carve(const setok_detok* d, int B, int cap, Arena& a, DetokBufs* o) {
+  const size_t R = static_cast<size_t>(B) * d->grid * d->grid;
+  const size_t H = d->hidden, Dd = d->dec_dim;
+  const size_t W = H > Dd ? H : Dd;
+  const size_t U = static_cast<size_t>(d->q_inter > d->dec_mlp ? d->q_inter : d->dec_mlp);
+  o->tokb = a.take<bf16>(static_cast<size_t>(cap) * d->token_dim);
+  o->enc = a.take<bf16>(static_cast<size_t>(cap) * H);
+  o->kv = a.take<bf16>(static_cast<size_t>(cap) * 2 * H);
+  o->idx = a.take<int32_t>(R);
+  o->h = a.take<bf16>(R * H);
+  o->a = a.take<bf16>(R * H);
+  o->q = a.take<bf16>(R * H);
+  o->qkv = a.take<bf16>(R * 3 * W);
+  o->ctx = a.take<bf16>(R * W);
+  o->u = a.take<bf16>(R * U);
+  o->x = a.take<bf16>(R * Dd);
+  o->hx = a.take<bf16>(R * Dd);
+  o->t32 = a.take<float>(R * W);
+}
+}  // namespace
+
+extern "C" size_t setok_detok_workspace_bytes(const setok_detok* d, int B, int rows_capacity) {
+  if (d == nullptr || B <= 0 || rows_capacity <= 0 || d->grid <= 0) return 0;
+  Arena a(nullptr, 0);
+  DetokBufs b;
+  detok_carve(d, B, rows_capacity, a, &b);
+  return a.off;
+}
+
+extern "C" int setok_detok_forward(const setok_detok* d, const void* tokens, int token_dtype, const int32_t* offsets, int B, int cap,
+                                   void* out, int out_dtype, void* workspace, size_t workspace_bytes, setok_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SETOK_REQUIRE(d && tokens && offsets && out, SETOK_ERR_BAD_ARG, "detok_forward: null pointer");
+  SETOK_REQUIRE(B > 0 && cap > 0 && d->grid > 0, SETOK_ERR_BAD_ARG, "detok_forward: B=%d rows_capacity=%d grid=%d", B, cap, d->grid);
+  const int Q = d->grid * d->grid, H = d->hidden, I = d->q_inter, Dd = d->dec_dim, Fd = d->dec_mlp, Ct = d->token_dim;
+  SETOK_REQUIRE(H > 0 && d->q_heads > 0 && H % d->q_heads == 0 && (H / d->q_heads) % 8 == 0 && H % 8 == 0 && I % 8 == 0 && Ct % 8 == 0,
+                SETOK_ERR_UNSUPPORTED, "detok_forward: Q-Former hidden %d heads %d inter %d token_dim %d unsupported", H, d->q_heads, I, Ct);
+  SETOK_REQUIRE(Dd > 0 && d->dec_heads > 0 && Dd % d->dec_heads == 0 && (Dd / d->dec_heads) % 8 == 0 && Dd % 8 == 0 && Fd % 8 == 0,
+                SETOK_ERR_UNSUPPORTED, "detok_forward: decoder dim %d heads %d mlp %d unsupported", Dd, d->dec_heads, Fd);
+  SETOK_REQUIRE(d->w_map_in && d->b_map_in && d->mask_tokens && d->emb_ln_g && d->emb_ln_b && (d->q_layers == 0 || d->qlayer) && d->w_dec_in &&
+                d->b_dec_in && d->pos && (d->dec_depth == 0 || d->block) && d->norm_g && d->norm_b, SETOK_ERR_BAD_ARG, "detok_forward: null weights");
+  SETOK_REQUIRE(token_dtype == SETOK_F32 || token_dtype == SETOK_BF16, SETOK_ERR_BAD_ARG, "detok_forward: bad token dtype %d", token_dtype);
+  SETOK_REQUIRE(workspace && workspace_bytes >= setok_detok_workspace_bytes(d, B, cap), SETOK_ERR_WORKSPACE, "detok_forward: workspace too small");
+  const int R = B * Q;
+  Arena ar(workspace, workspace_bytes);
+  DetokBufs w;
+  detok_carve(d, B, cap, ar, &w);
+  const int32_t* n_tok = offsets + B;                      // device scalar: sum_b K_b
+  const float qscale = 1.0f / std::sqrt(static_cast<float>(H / d->q_heads));
+
+  // detokenizer.py:104: encoder states = mapper_fc_in(tokens), over the packed rows
+  const void* tok = tokens;
+  if (token_dtype == SETOK_F32) {
+    SETOK_TRY(launch_convert_rows(tokens, SETOK_F32, w.tokb, SETOK_BF16, cap, Ct, SETOK_ACT_NONE, n_tok, stream));
+    tok = w.tokb;
+  }
+  SETOK_TRY(launch_gemm(GemmArgs{tok, Ct, d->w_map_in, Ct, w.enc, H, SETOK_BF16, d->b_map_in, nullptr, 0, 0, SETOK_ACT_NONE, cap, H, Ct, n_tok, 0}, stream));
+  // BertEmbeddings (module.py:203-205): LayerNorm of the learned queries, replicated per image
+  SETOK_TRY(launch_iota_mod(w.idx, R, Q, stream));
+  SETOK_TRY(launch_layernorm(d->mask_tokens, SETOK_F32, w.h, SETOK_BF16, d->emb_ln_g, d->emb_ln_b, d->q_ln_eps, R, H, w.idx, nullptr, stream));
+
+  for (int l = 0; l < d->q_layers; ++l) {
+    const setok_qformer_layer& L = d->qlayer[l];
+    SETOK_REQUIRE(L.w_qkv && L.b_qkv && L.w_so && L.b_so && L.ln_s_g && L.ln_s_b && L.w_f1 && L.b_f1 && L.w_f2 && L.b_f2 && L.ln_f_g && L.ln_f_b,
+                  SETOK_ERR_BAD_ARG, "detok_forward: null weights in Q-Former layer %d", l);
+    // self-attention among the queries + BertSelfOutput (post-LN, module.py:383-387)
+    SETOK_TRY(launch_gemm(GemmArgs{w.h, H, L.w_qkv, H, w.qkv, 3LL * H, SETOK_BF16, L.b_qkv, nullptr, 0, 0, SETOK_ACT_NONE, R, 3 * H, H, nullptr, 0}, stream));
+    SETOK_TRY(launch_attention(w.qkv, w.ctx, R, H, d->q_heads, qscale, nullptr, nullptr, Q, nullptr, stream));
+    SETOK_TRY(launch_gemm(GemmArgs{w.ctx, H, L.w_so, H, w.t32, H, SETOK_F32, L.b_so, w.h, H, SETOK_BF16, SETOK_ACT_NONE, R, H, H, nullptr, 0}, stream));
+    SETOK_TRY(launch_layernorm(w.t32, SETOK_F32, w.a, SETOK_BF16, L.ln_s_g, L.ln_s_b, d->q_ln_eps, R, H, nullptr, nullptr, stream));
+    if (L.has_cross) {
+      SETOK_REQUIRE(L.w_cq && L.b_cq && L.w_ckv && L.b_ckv && L.w_co && L.b_co && L.ln_c_g && L.ln_c_b, SETOK_ERR_BAD_ARG,
+                    "detok_forward: null cross-attention weights in Q-Former layer %d", l);
+      // cross-attention to the image's own K_b tokens (module.py:528-544), varlen over the packed rows
+      SETOK_TRY(launch_gemm(GemmArgs{w.a, H, L.w_cq, H, w.q, H, SETOK_BF16, L.b_cq, nullptr, 0, 0, SETOK_ACT_NONE, R, H, H, nullptr, 0}, stream));
+      SETOK_TRY(launch_gemm(GemmArgs{w.enc, H, L.w_ckv, H, w.kv, 2LL * H, SETOK_BF16, L.b_ckv, nullptr, 0, 0, SETOK_ACT_NONE, cap, 2 * H, H, n_tok, 0}, stream));
+      SETOK_TRY(launch_cross_attention(w.q, w.kv, w.ctx, R, Q, H, d->q_heads, qscale, offsets, stream));
+      SETOK_TRY(launch_gemm(GemmArgs{w.ctx, H, L.w_co, H, w.t32, H, SETOK_F32, L.b_co, w.a, H, SETOK_BF16, SETOK_ACT_NONE, R, H, H, nullptr, 0}, stream));
+      SETOK_TRY(launch_layernorm(w.t32, SETOK_F32, w.a, SETOK_BF16, L.ln_c_g, L.ln_c_b, d->q_ln_eps, R, H, nullptr, nullptr, stream));
+    }
+    // query FFN (module.py:579-582)
+    SETOK_TRY(launch_gemm(GemmArgs{w.a, H, L.w_f1, H, w.u, I, SETOK_BF16, L.b_f1, nullptr, 0, 0, SETOK_ACT_GELU_ERF, R, I, H, nullptr, 0}, stream));
+    SETOK_TRY(launch_gemm(GemmArgs{w.u, I, L.w_f2, I, w.t32, H, SETOK_F32, L.b_f2, w.a, H, SETOK_BF16, SETOK_ACT_NONE, R, H, I, nullptr, 0}, stream));
+    SETOK_TRY(launch_layernorm(w.t32, SETOK_F32, w.h, SETOK_BF16, L.ln_f_g, L.ln_f_b, d->q_ln_eps, R, H, nullptr, nullptr, stream));
+  }
+
+  // detokenizer.py:111-115: decoder_fc_in, + 2-D sincos position embedding
+  SETOK_TRY(launch_gemm(GemmArgs{w.h, H, d->w_dec_in, H, w.t32, Dd, SETOK_F32, d->b_dec_in, nullptr, 0, 0, SETOK_ACT_NONE, R, Dd, H, nullptr, 0}, stream));
+  SETOK_TRY(launch_add_pos_rows(w.t32, d->pos, w.x, R, Q, Dd, stream));
+  // :117-118 pixel_decoder (timm Block = pre-LN ViT layer with GELU(erf)); :120 decoder_norm
+  for (int l = 0; l < d->dec_depth; ++l) {
+    const setok_vit_layer& L = d->block[l];
+    SETOK_REQUIRE(L.w_qkv && L.b_qkv && L.w_o && L.b_o && L.w_fc1 && L.b_fc1 && L.w_fc2 && L.b_fc2 && L.ln1_g && L.ln1_b && L.ln2_g && L.ln2_b,
+                  SETOK_ERR_BAD_ARG, "detok_forward: null weights in decoder block %d", l);
+    SETOK_TRY(run_preln_layer(L, w.x, w.hx, w.qkv, w.ctx, w.u, R, Q, Dd, Fd, d->dec_heads, d->dec_ln_eps, SETOK_ACT_GELU_ERF, stream));
+  }
+  SETOK_TRY(launch_layernorm(w.x, SETOK_BF16, out, out_dtype, d->norm_g, d->norm_b, d->dec_ln_eps, R, Dd, nullptr, nullptr, stream));
   return SETOK_OK;
 }

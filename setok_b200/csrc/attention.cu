@@ -21,23 +21,27 @@ __device__ __forceinline__ int live_rows_a(int rows, const int32_t* m_dev) {
 // -------------------------------------------------------------------------------------------------
 // ragged segments, any head_dim % 8 == 0, <= 512
 // -------------------------------------------------------------------------------------------------
+// Queries at q + r*ldq, keys / values at kp / vp + j*ldkv.  Self-attention over a fused qkv buffer passes q = qkv,
+// kp = qkv + C, vp = qkv + 2C, ldq = ldkv = 3C.  cross_Q > 0: cross-attention, query row r belongs to image r / cross_Q
+// and attends to the packed key rows [seg_off[image], seg_off[image + 1]) (the ragged token batch: no padding mask).
 template <int VPL>
-__global__ void __launch_bounds__(256) attn_seg_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int rows, int C,
+__global__ void __launch_bounds__(256) attn_seg_kernel(const bf16* __restrict__ qp, long long ldq, const bf16* __restrict__ kp,
+                                                       const bf16* __restrict__ vp, long long ldkv, bf16* __restrict__ out, int rows, int C,
                                                        int heads, float scale, const int32_t* __restrict__ seg_off,
-                                                       const int32_t* __restrict__ row_seg, int uniform_T,
+                                                       const int32_t* __restrict__ row_seg, int uniform_T, int cross_Q,
                                                        const int32_t* __restrict__ m_dev) {
   const int lane = threadIdx.x & 31;
   const int n = live_rows_a(rows, m_dev);
   const long long total = static_cast<long long>(n) * heads;
   const int hd = C / heads;
   const int nv = hd >> 3;
-  const long long ld = 3LL * C;
   for (long long wid = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); wid < total;
        wid += static_cast<long long>(gridDim.x) * (blockDim.x >> 5)) {
     const int r = static_cast<int>(wid / heads);
     const int h = static_cast<int>(wid % heads);
     int s0, s1;
-    if (uniform_T > 0) { s0 = (r / uniform_T) * uniform_T; s1 = s0 + uniform_T; }
+    if (cross_Q > 0) { const int s = r / cross_Q; s0 = seg_off[s]; s1 = seg_off[s + 1]; }
+    else if (uniform_T > 0) { s0 = (r / uniform_T) * uniform_T; s1 = s0 + uniform_T; }
     else { const int s = row_seg[r]; s0 = seg_off[s]; s1 = seg_off[s + 1]; }
     float q[VPL][8], o[VPL][8];
 #pragma unroll
@@ -46,7 +50,7 @@ __global__ void __launch_bounds__(256) attn_seg_kernel(const bf16* __restrict__ 
 #pragma unroll
       for (int e = 0; e < 8; ++e) { q[i][e] = 0.f; o[i][e] = 0.f; }
       if (vi < nv) {
-        const uint4 u = *reinterpret_cast<const uint4*>(qkv + r * ld + h * hd + vi * 8);
+        const uint4 u = *reinterpret_cast<const uint4*>(qp + r * ldq + h * hd + vi * 8);
         const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
         q[i][0] = a.x * scale; q[i][1] = a.y * scale; q[i][2] = b.x * scale; q[i][3] = b.y * scale;
         q[i][4] = c.x * scale; q[i][5] = c.y * scale; q[i][6] = d.x * scale; q[i][7] = d.y * scale;
@@ -64,7 +68,7 @@ __global__ void __launch_bounds__(256) attn_seg_kernel(const bf16* __restrict__ 
           for (int i = 0; i < VPL; ++i) {
             const int vi = lane + 32 * i;
             if (vi < nv) {
-              const uint4 u = *reinterpret_cast<const uint4*>(qkv + jj * ld + C + h * hd + vi * 8);
+              const uint4 u = *reinterpret_cast<const uint4*>(kp + jj * ldkv + h * hd + vi * 8);
               const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
               part += q[i][0] * a.x + q[i][1] * a.y + q[i][2] * b.x + q[i][3] * b.y + q[i][4] * c.x + q[i][5] * c.y +
                       q[i][6] * d.x + q[i][7] * d.y;
@@ -99,7 +103,7 @@ __global__ void __launch_bounds__(256) attn_seg_kernel(const bf16* __restrict__ 
           for (int i = 0; i < VPL; ++i) {
             const int vi = lane + 32 * i;
             if (vi < nv) {
-              const uint4 u = *reinterpret_cast<const uint4*>(qkv + jj * ld + 2 * C + h * hd + vi * 8);
+              const uint4 u = *reinterpret_cast<const uint4*>(vp + jj * ldkv + h * hd + vi * 8);
               const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
               o[i][0] += p[u4] * a.x; o[i][1] += p[u4] * a.y; o[i][2] += p[u4] * b.x; o[i][3] += p[u4] * b.y;
               o[i][4] += p[u4] * c.x; o[i][5] += p[u4] * c.y; o[i][6] += p[u4] * d.x; o[i][7] += p[u4] * d.y;
@@ -108,7 +112,7 @@ __global__ void __launch_bounds__(256) attn_seg_kernel(const bf16* __restrict__ 
         }
       }
     }
-    const float inv = 1.0f / l;
+    const float inv = l > 0.f ? 1.0f / l : 0.f;     // an empty key segment yields zeros
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int vi = lane + 32 * i;
@@ -142,10 +146,33 @@ int launch_attention(const void* qkv, void* out, int rows, int C, int heads, flo
   long long blocks = (warps + 7) / 8;
   const long long cap = static_cast<long long>(num_sms()) * 32;
   if (blocks > cap) blocks = cap;
+  const bf16* q = static_cast<const bf16*>(qkv);
   if (hd <= 256)
-    attn_seg_kernel<1><<<static_cast<int>(blocks), 256, 0, stream>>>(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), rows, C, heads, scale, seg_off, row_seg, uniform_T, m_dev);
+    attn_seg_kernel<1><<<static_cast<int>(blocks), 256, 0, stream>>>(q, 3LL * C, q + C, q + 2 * C, 3LL * C, static_cast<bf16*>(out), rows, C, heads, scale, seg_off, row_seg, uniform_T, 0, m_dev);
   else
-    attn_seg_kernel<2><<<static_cast<int>(blocks), 256, 0, stream>>>(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), rows, C, heads, scale, seg_off, row_seg, uniform_T, m_dev);
+    attn_seg_kernel<2><<<static_cast<int>(blocks), 256, 0, stream>>>(q, 3LL * C, q + C, q + 2 * C, 3LL * C, static_cast<bf16*>(out), rows, C, heads, scale, seg_off, row_seg, uniform_T, 0, m_dev);
+  SETOK_LAUNCH_CHECK();
+  return SETOK_OK;
+}
+
+// Cross-attention of `rows` = B * Q query rows (q [rows, C]) over the ragged key/value rows kv [*, 2C] (keys in columns
+// [0, C), values in [C, 2C)): query row r sees rows [offsets[r / Q], offsets[r / Q + 1]).
+int launch_cross_attention(const void* q, const void* kv, void* out, int rows, int Q, int C, int heads, float scale,
+                           const int32_t* offsets, cudaStream_t stream) {
+  SETOK_REQUIRE(q && kv && out && offsets, SETOK_ERR_BAD_ARG, "cross_attention: null pointer");
+  SETOK_REQUIRE(rows > 0 && Q > 0 && rows % Q == 0 && C > 0 && heads > 0 && C % heads == 0, SETOK_ERR_BAD_ARG, "cross_attention: bad shape rows=%d Q=%d C=%d heads=%d", rows, Q, C, heads);
+  const int hd = C / heads;
+  SETOK_REQUIRE(hd % 8 == 0 && hd <= 512, SETOK_ERR_UNSUPPORTED, "cross_attention: head_dim %d unsupported (need %%8==0, <=512)", hd);
+  SETOK_REQUIRE(aligned16(q) && aligned16(kv) && aligned16(out), SETOK_ERR_BAD_ARG, "cross_attention: buffers must be 16-byte aligned");
+  const long long warps = static_cast<long long>(rows) * heads;
+  long long blocks = (warps + 7) / 8;
+  const long long cap = static_cast<long long>(num_sms()) * 32;
+  if (blocks > cap) blocks = cap;
+  const bf16* k = static_cast<const bf16*>(kv);
+  if (hd <= 256)
+    attn_seg_kernel<1><<<static_cast<int>(blocks), 256, 0, stream>>>(static_cast<const bf16*>(q), C, k, k + C, 2LL * C, static_cast<bf16*>(out), rows, C, heads, scale, offsets, nullptr, 0, Q, nullptr);
+  else
+    attn_seg_kernel<2><<<static_cast<int>(blocks), 256, 0, stream>>>(static_cast<const bf16*>(q), C, k, k + C, 2LL * C, static_cast<bf16*>(out), rows, C, heads, scale, offsets, nullptr, 0, Q, nullptr);
   SETOK_LAUNCH_CHECK();
   return SETOK_OK;
 }

@@ -348,6 +348,40 @@ int launch_cls_rows(float* emb, const float* cls, const float* pos, int B, int T
   return SETOK_OK;
 }
 
+// idx[r] = r % Q: gather indices that replicate a (Q, C) table for every image of a batch
+__global__ void iota_mod_kernel(int32_t* __restrict__ idx, int rows, int Q) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) idx[r] = r % Q;
+}
+
+// out[r, :] (bf16) = in[r, :] (f32) + pos[r % Q, :]
+__global__ void __launch_bounds__(256) add_pos_rows_kernel(const float* __restrict__ in, const float* __restrict__ pos, bf16* __restrict__ out,
+                                                           int rows, int Q, int C) {
+  const int nvec = C >> 2;
+  const long long total = static_cast<long long>(rows) * nvec;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int vi = static_cast<int>(i % nvec);
+    const long long r = i / nvec;
+    float4 v = reinterpret_cast<const float4*>(in)[i];
+    const float4 q = __ldg(reinterpret_cast<const float4*>(pos + (r % Q) * C + vi * 4));
+    v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+    Vec4<bf16>::store(out + (r * C + vi * 4), v);
+  }
+}
+
+int launch_iota_mod(int32_t* idx, int rows, int Q, cudaStream_t stream) {
+  iota_mod_kernel<<<grid_for(rows, 256, 4), 256, 0, stream>>>(idx, rows, Q);
+  SETOK_LAUNCH_CHECK();
+  return SETOK_OK;
+}
+
+int launch_add_pos_rows(const float* in, const float* pos, void* out_bf16, int rows, int Q, int C, cudaStream_t stream) {
+  SETOK_REQUIRE(C % 4 == 0, SETOK_ERR_UNSUPPORTED, "add_pos_rows: C (%d) must be a multiple of 4", C);
+  add_pos_rows_kernel<<<grid_for(static_cast<long long>(rows) * (C / 4), 256, 16), 256, 0, stream>>>(in, pos, static_cast<bf16*>(out_bf16), rows, Q, C);
+  SETOK_LAUNCH_CHECK();
+  return SETOK_OK;
+}
+
 int launch_select_rows(const void* x_bf16, void* out, int out_dtype, int B, int T, int skip, int C, const float* pos, cudaStream_t stream) {
   const long long total = static_cast<long long>(B) * (T - skip) * (C / 4);
   const int grid = grid_for(total, 256, 16);

@@ -17,5 +17,7 @@ int launch_convert_rows(const void* in, int in_dtype, void* out, int out_dtype, 
                         cudaStream_t stream);
 int launch_masked_softmax(const float* S, void* P, const int32_t* seg_off, const int32_t* row_seg, int rows, int N, int ldS, int ldP,
                           float scale, cudaStream_t stream);
+int launch_iota_mod(int32_t* idx, int rows, int Q, cudaStream_t stream);
+int launch_add_pos_rows(const float* in, const float* pos, void* out_bf16, int rows, int Q, int C, cudaStream_t stream);
 int get_pos_table(int h, int w, int C, const float** out, cudaStream_t stream);
 }  // namespace setok
