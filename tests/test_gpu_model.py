@@ -315,6 +315,21 @@ def test_config3_tokenizer_at_336_bf16():
     assert _err(got, ref)[1] < 1.5e-2
     rt, idx, score = tok(imgs.to(DEV, torch.bfloat16), k=16)
     assert rt.dtype == torch.bfloat16 and idx.shape == (B, 576) and all(1 <= c <= 576 for c in rt.counts)
+    # configs[2], decoder half: the detokenizer consumes the ragged batch as it is (detokenizer.py:101-120): 576 learned
+    # queries (336/14)^2 cross-attend each image's own K_b tokens; hidden 768 / 12 heads (training_utils.py:55-56)
+    from oracle import detok_oracle as D
+    from setok_b200 import SetokDeTokenizer
+    d = dict(token_dim=C, hidden=768, q_heads=12, q_inter=3072, q_layers=2, cross_freq=2, grid=24, dec_dim=768, dec_depth=2, dec_mlp=3072)
+    dp = D.make_detok_params(**d, seed=34)
+    det = SetokDeTokenizer(token_feat_dim=C, hidden_dim=768, patch_size=14, image_size=336, decoder_embed_dim=768, decoder_nheads=12,
+                           decoder_depth=2, num_hidden_layers=2, cross_attention_freq=2)
+    assert not det.load_state_dict(dp, strict=False).unexpected_keys
+    det = det.to(DEV)
+    recon = det(rt)
+    assert recon.shape == (B, 576, 768) and recon.dtype == torch.bfloat16 and bool(torch.isfinite(recon.float()).all())
+    x, m = D.pad_ragged(rt.packed().float().cpu(), [int(v) for v in rt.offsets.cpu()])
+    ref_recon = D.detok_forward(dp, x, m, q_heads=12, q_layers=2, cross_freq=2, grid=24, dec_heads=12, dec_depth=2, hidden=768)
+    assert _err(recon, ref_recon)[1] < 1e-2
 
 
 def test_config4_encode_images_to_vicuna_projector_bf16():
