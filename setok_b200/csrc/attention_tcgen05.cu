@@ -56,6 +56,7 @@ attn_tcgen05_hd64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_co
   uint8_t* smem = smem_raw;
   if ((base & 1023u) != 0u) __trap();   // the 128B-swizzled tiles need a 1 KiB aligned window
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int q0 = qt * QT;
   const int nchunks = (T + KT - 1) / KT;
@@ -80,6 +81,7 @@ attn_tcgen05_hd64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_co
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_wait();                                   // qkv comes from the previous kernel of the stream
   if (threadIdx.x == 0) TRACE(1);
 
   if (warp == W_TMA) {
@@ -295,7 +297,8 @@ int launch_attention_tcgen05(const void* qkv, void* out, int B, int T, int C, in
   std::call_once(once, [] { attr_err = cudaFuncSetAttribute(attn_tcgen05_hd64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM); });
   SETOK_CUDA_OK(attr_err);
   dim3 grid(ceil_div(T, QT), heads, B);
-  attn_tcgen05_hd64_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tm, tm_kv, static_cast<bf16*>(out), T, heads, C, scale * 1.4426950408889634f, g_attn_trace);
+  SETOK_CUDA_OK(launch_pdl(attn_tcgen05_hd64_kernel, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tm, tm_kv, static_cast<bf16*>(out), T, heads, C,
+                           scale * 1.4426950408889634f, g_attn_trace));
   SETOK_LAUNCH_CHECK();
   return SETOK_OK;
 }

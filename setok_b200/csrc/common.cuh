@@ -130,6 +130,13 @@ __device__ __forceinline__ float act_quick_gelu(float x) {
 }
 __device__ __forceinline__ float act_gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
+// ---- programmatic dependent launch ------------------------------------------------------------
+// Kernels launched with cudaLaunchAttributeProgrammaticStreamSerialization may start (prologue: barrier init, TMEM
+// allocation, descriptor prefetch) while the previous kernel of the stream is still draining; pdl_wait() returns once that
+// kernel has completed and its writes are visible.  Both are no-ops for a normally launched kernel.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- mbarrier ------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -384,6 +391,19 @@ struct GemmArgs {
   int w_mn_major = 0;
 };
 int launch_gemm(const GemmArgs& g, cudaStream_t stream);
+extern int g_pdl;   // 1: launch the tower's kernels with programmatic stream serialization (setok_debug_set_pdl)
+
+// <<<>>> with the programmatic-stream-serialization attribute (the kernel must call pdl_wait() before it touches memory)
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // dpc_fused.cu: whole clustering (a3+a4) in one persistent kernel for N <= 256
 bool dpc_fused_supported(int N, int C, int k);

@@ -5,6 +5,7 @@ namespace setok {
 
 static thread_local char t_error[512] = "";
 std::atomic<uint64_t> g_launches{0};
+int g_pdl = 1;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -28,3 +29,4 @@ int num_sms() {
 extern "C" const char* setok_last_error(void) { return setok::t_error; }
 extern "C" int setok_abi_version(void) { return 1; }
 extern "C" uint64_t setok_launch_count(void) { return setok::g_launches.load(std::memory_order_relaxed); }
+extern "C" void setok_debug_set_pdl(int on) { setok::g_pdl = on; }

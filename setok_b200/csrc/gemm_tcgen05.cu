@@ -74,6 +74,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();            // the next kernel of the stream may set itself up while this one runs
 
   const uint32_t bar0 = base + OFF_BAR;
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
@@ -99,6 +100,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_wait();                         // operands, residual and the device row count come from earlier kernels of the stream
 
   int M_eff = p.M;
   if (p.m_dev != nullptr) { int m = *p.m_dev; M_eff = m < p.M ? (m < 0 ? 0 : m) : p.M; }
@@ -424,11 +426,13 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   cfg.blockDim = dim3(THREADS);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cg; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   SETOK_CUDA_OK(cudaLaunchKernelEx(&cfg, fn, tmA, tmB, p));
   SETOK_LAUNCH_CHECK();
   return SETOK_OK;

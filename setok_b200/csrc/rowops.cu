@@ -39,6 +39,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const TI* __restrict__ i
                                                         const int32_t* __restrict__ m_dev) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
+  pdl_launch_dependents();
+  pdl_wait();
   const int n = live_rows(rows, m_dev);
   const int nvec = C >> 2;
   const bool cached = nvec <= LN_MAXV * 32;
@@ -311,7 +313,7 @@ int launch_layernorm(const void* in, int in_dtype, void* out, int out_dtype, con
   int grid = ceil_div(rows, wpb);
   const int cap = num_sms() * 8;
   if (grid > cap) grid = cap;
-#define LN_CASE(TI, TO) layernorm_kernel<TI, TO><<<grid, wpb * 32, 0, stream>>>(static_cast<const TI*>(in), static_cast<TO*>(out), gamma, beta, eps, rows, C, gather, m_dev)
+#define LN_CASE(TI, TO) SETOK_CUDA_OK(launch_pdl(layernorm_kernel<TI, TO>, dim3(grid), dim3(wpb * 32), 0, stream, static_cast<const TI*>(in), static_cast<TO*>(out), gamma, beta, eps, rows, C, gather, m_dev))
   if (in_dtype == SETOK_F32 && out_dtype == SETOK_F32) LN_CASE(float, float);
   else if (in_dtype == SETOK_F32 && out_dtype == SETOK_BF16) LN_CASE(float, bf16);
   else if (in_dtype == SETOK_BF16 && out_dtype == SETOK_BF16) LN_CASE(bf16, bf16);
