@@ -126,6 +126,106 @@ __global__ void __launch_bounds__(256) attn_seg_kernel(const bf16* __restrict__ 
   }
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// cross-attention, head_dim 64 (the Q-Former's BERT heads): one thread per query, the image's keys / values stream
+// through shared memory as fp32 in chunks of 64 (every lane of a warp reads the same K/V row: 16-byte broadcasts),
+// scores in groups of 8 keys, online softmax in the exp2 domain.  Grid (head, image, query block).
+// -------------------------------------------------------------------------------------------------
+constexpr int XA_HD = 64, XA_KC = 64, XA_THREADS = 192;
+
+__global__ void __launch_bounds__(XA_THREADS) cross_attn_hd64_kernel(const bf16* __restrict__ q, const bf16* __restrict__ kv, bf16* __restrict__ out,
+                                                                     int Q, int C, float scale_log2, const int32_t* __restrict__ offsets) {
+  __shared__ __align__(16) float Ks[XA_KC][XA_HD];
+  __shared__ __align__(16) float Vs[XA_KC][XA_HD];
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int qi = blockIdx.z * XA_THREADS + threadIdx.x;
+  const bool live = qi < Q;
+  const int s0 = offsets[b], s1 = offsets[b + 1];
+  const long long qrow = static_cast<long long>(b) * Q + (live ? qi : 0);
+  float qv[XA_HD], o[XA_HD];
+#pragma unroll
+  for (int c = 0; c < XA_HD / 8; ++c) {
+    const uint4 u = *reinterpret_cast<const uint4*>(q + qrow * C + h * XA_HD + c * 8);
+    const float2 a = unpack_bf16x2(u.x), b2 = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z), d2 = unpack_bf16x2(u.w);
+    qv[c * 8 + 0] = a.x * scale_log2; qv[c * 8 + 1] = a.y * scale_log2; qv[c * 8 + 2] = b2.x * scale_log2; qv[c * 8 + 3] = b2.y * scale_log2;
+    qv[c * 8 + 4] = c2.x * scale_log2; qv[c * 8 + 5] = c2.y * scale_log2; qv[c * 8 + 6] = d2.x * scale_log2; qv[c * 8 + 7] = d2.y * scale_log2;
+  }
+#pragma unroll
+  for (int d = 0; d < XA_HD; ++d) o[d] = 0.f;
+  float m = -INFINITY, l = 0.f;
+  const long long ldkv = 2LL * C;
+  for (int k0 = s0; k0 < s1; k0 += XA_KC) {
+    const int nk = min(XA_KC, s1 - k0);
+    const int nk8 = (nk + 7) & ~7;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nk8 * (XA_HD / 8); idx += XA_THREADS) {
+      const int key = idx / (XA_HD / 8), c = idx % (XA_HD / 8);
+      float kf[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, vf[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (key < nk) {
+        const bf16* src = kv + (k0 + key) * ldkv + h * XA_HD + c * 8;
+        const uint4 uk = *reinterpret_cast<const uint4*>(src);
+        const uint4 uv = *reinterpret_cast<const uint4*>(src + C);
+        const float2 k0f = unpack_bf16x2(uk.x), k1f = unpack_bf16x2(uk.y), k2f = unpack_bf16x2(uk.z), k3f = unpack_bf16x2(uk.w);
+        const float2 v0f = unpack_bf16x2(uv.x), v1f = unpack_bf16x2(uv.y), v2f = unpack_bf16x2(uv.z), v3f = unpack_bf16x2(uv.w);
+        kf[0] = k0f.x; kf[1] = k0f.y; kf[2] = k1f.x; kf[3] = k1f.y; kf[4] = k2f.x; kf[5] = k2f.y; kf[6] = k3f.x; kf[7] = k3f.y;
+        vf[0] = v0f.x; vf[1] = v0f.y; vf[2] = v1f.x; vf[3] = v1f.y; vf[4] = v2f.x; vf[5] = v2f.y; vf[6] = v3f.x; vf[7] = v3f.y;
+      }
+      *reinterpret_cast<float4*>(&Ks[key][c * 8]) = make_float4(kf[0], kf[1], kf[2], kf[3]);
+      *reinterpret_cast<float4*>(&Ks[key][c * 8 + 4]) = make_float4(kf[4], kf[5], kf[6], kf[7]);
+      *reinterpret_cast<float4*>(&Vs[key][c * 8]) = make_float4(vf[0], vf[1], vf[2], vf[3]);
+      *reinterpret_cast<float4*>(&Vs[key][c * 8 + 4]) = make_float4(vf[4], vf[5], vf[6], vf[7]);
+    }
+    __syncthreads();
+    for (int kk = 0; kk < nk8; kk += 8) {
+      float sc[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int d = 0; d < XA_HD; d += 8) {
+          const float4 k4 = *reinterpret_cast<const float4*>(&Ks[kk + u][d]);
+          const float4 k5 = *reinterpret_cast<const float4*>(&Ks[kk + u][d + 4]);
+          a0 = fmaf(qv[d], k4.x, a0); a1 = fmaf(qv[d + 1], k4.y, a1); a0 = fmaf(qv[d + 2], k4.z, a0); a1 = fmaf(qv[d + 3], k4.w, a1);
+          a0 = fmaf(qv[d + 4], k5.x, a0); a1 = fmaf(qv[d + 5], k5.y, a1); a0 = fmaf(qv[d + 6], k5.z, a0); a1 = fmaf(qv[d + 7], k5.w, a1);
+        }
+        sc[u] = kk + u < nk ? a0 + a1 : -INFINITY;
+      }
+      float mx = sc[0];
+#pragma unroll
+      for (int u = 1; u < 8; ++u) mx = fmaxf(mx, sc[u]);
+      const float m_new = fmaxf(m, mx);
+      const float alpha = exp2f(m - m_new);
+      float psum = 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { sc[u] = exp2f(sc[u] - m_new); psum += sc[u]; }
+      l = l * alpha + psum;
+      m = m_new;
+#pragma unroll
+      for (int d = 0; d < XA_HD; ++d) o[d] *= alpha;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+#pragma unroll
+        for (int d = 0; d < XA_HD; d += 4) {
+          const float4 v4 = *reinterpret_cast<const float4*>(&Vs[kk + u][d]);
+          o[d] = fmaf(sc[u], v4.x, o[d]); o[d + 1] = fmaf(sc[u], v4.y, o[d + 1]); o[d + 2] = fmaf(sc[u], v4.z, o[d + 2]); o[d + 3] = fmaf(sc[u], v4.w, o[d + 3]);
+        }
+      }
+    }
+  }
+  if (live) {
+    const float inv = l > 0.f ? 1.0f / l : 0.f;       // an empty key segment yields zeros
+    bf16* dst = out + (static_cast<long long>(b) * Q + qi) * C + h * XA_HD;
+#pragma unroll
+    for (int c = 0; c < XA_HD / 8; ++c) {
+      uint4 u;
+      u.x = pack_bf16x2(o[c * 8 + 0] * inv, o[c * 8 + 1] * inv); u.y = pack_bf16x2(o[c * 8 + 2] * inv, o[c * 8 + 3] * inv);
+      u.z = pack_bf16x2(o[c * 8 + 4] * inv, o[c * 8 + 5] * inv); u.w = pack_bf16x2(o[c * 8 + 6] * inv, o[c * 8 + 7] * inv);
+      *reinterpret_cast<uint4*>(dst + c * 8) = u;
+    }
+  }
+}
+
 }  // namespace
 
 int launch_attention(const void* qkv, void* out, int rows, int C, int heads, float scale, const int32_t* seg_off,
@@ -164,6 +264,13 @@ int launch_cross_attention(const void* q, const void* kv, void* out, int rows, i
   const int hd = C / heads;
   SETOK_REQUIRE(hd % 8 == 0 && hd <= 512, SETOK_ERR_UNSUPPORTED, "cross_attention: head_dim %d unsupported (need %%8==0, <=512)", hd);
   SETOK_REQUIRE(aligned16(q) && aligned16(kv) && aligned16(out), SETOK_ERR_BAD_ARG, "cross_attention: buffers must be 16-byte aligned");
+  if (hd == XA_HD) {
+    dim3 grid(heads, rows / Q, ceil_div(Q, XA_THREADS));
+    cross_attn_hd64_kernel<<<grid, XA_THREADS, 0, stream>>>(static_cast<const bf16*>(q), static_cast<const bf16*>(kv), static_cast<bf16*>(out), Q, C,
+                                                            scale * 1.4426950408889634f, offsets);
+    SETOK_LAUNCH_CHECK();
+    return SETOK_OK;
+  }
   const long long warps = static_cast<long long>(rows) * heads;
   long long blocks = (warps + 7) / 8;
   const long long cap = static_cast<long long>(num_sms()) * 32;

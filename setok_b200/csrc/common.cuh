@@ -128,7 +128,21 @@ __device__ __forceinline__ float act_quick_gelu(float x) {
   const float hx = 0.5f * x;
   return fmaf(hx, t, hx);
 }
-__device__ __forceinline__ float act_gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7 absolute, i.e. far below the bf16
+// rounding of every consumer): one MUFU.RCP + one MUFU.EX2 + a degree-5 Horner chain instead of erff()'s branchy ~30
+// instructions -- the GELU GEMM epilogues (head / projector / detokenizer fc1) are issue-bound, not tensor-bound
+__device__ __forceinline__ float act_gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float erf_abs = fmaf(-p * t, e, 1.0f);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
 
 // ---- programmatic dependent launch ------------------------------------------------------------
 // Kernels launched with cudaLaunchAttributeProgrammaticStreamSerialization may start (prologue: barrier init, TMEM

@@ -392,6 +392,7 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
     else if (g.act == SETOK_ACT_GELU_ERF && res_kind == 0 && !out_f32) fn = SETOK_PICK(2, 0, 0, 0);     // head / projector fc1
     else if (g.act == SETOK_ACT_NONE && res_kind == 2 && out_f32) fn = SETOK_PICK(0, 2, 1, 0);          // head proj / fc2
     else if (g.act == SETOK_ACT_NONE && res_kind == 0 && out_f32) fn = SETOK_PICK(0, 0, 1, 0);          // out / projector last
+    else if (g.act == SETOK_ACT_NONE && res_kind == 1 && out_f32) fn = SETOK_PICK(0, 1, 1, 0);          // Q-Former dense + residual -> post-LN
   } else if (g.act == SETOK_ACT_NONE && res_kind == 2 && out_f32) {
     fn = SETOK_PICK(0, 2, 1, 1);                                                                         // patch embedding
   }
