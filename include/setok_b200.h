@@ -246,6 +246,28 @@ int setok_detok_forward(const setok_detok* detok, const void* tokens, int token_
                         int rows_capacity, void* out, int out_dtype, void* workspace, size_t workspace_bytes,
                         setok_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * a9 / SURVEY 8f row 2: the splice of SetokimMetaForCausalLM.prepare_inputs_labels_for_multimodal
+ * (src/model/setokim_arch.py:241-354) on the device: every IMAGE_TOKEN_INDEX (-200) placeholder of a sample is replaced
+ * by the K rows of the next image of the ragged batch, text ids go through the embedding table, labels are filled with
+ * IGNORE_INDEX (-100) over image rows (TARGET_TOKEN_INDEX -300 -> -100, :345), sequences are truncated to max_length
+ * (:307-310) and padded right or left to the batch maximum (:312-341).  A sample without a placeholder still consumes
+ * one image index (:262-269).  Replaces the per-sample Python loop, the boolean-mask compaction and the torch.cat chain.
+ *   input_ids      (device) int64 [B, L];  attention_mask (device) uint8 [B, L] or NULL (all valid);  labels int64 [B, L] or NULL
+ *   embed          (device) [V, H] f32|bf16: the LLM's embed_tokens weight;  image_rows (device) [*, H], same dtype
+ *   image_offsets  (device) int32 [n_images + 1]: rows [o[i], o[i+1]) are image i (RaggedTokens.offsets)
+ *   out_cap        row capacity T of the outputs: embeds [B, T, H], labels_out int64 [B, T], mask_out uint8 [B, T],
+ *                  pos_out int64 [B, T]; columns >= max_len are padding.  lens int32 [B] and max_len int32 [1] come back
+ *                  on the device (no host sync inside); a sequence longer than out_cap is truncated to it.
+ *   workspace      setok_splice_workspace_bytes(B, L, out_cap)
+ */
+size_t setok_splice_workspace_bytes(int B, int L, int out_cap);
+int setok_splice(const int64_t* input_ids, const uint8_t* attention_mask, const int64_t* labels, int B, int L,
+                 const void* embed, int dtype, int V, int H, const void* image_rows, const int32_t* image_offsets,
+                 int n_images, int max_length, int pad_left, int out_cap, void* embeds, int64_t* labels_out,
+                 uint8_t* mask_out, int64_t* pos_out, int32_t* lens, int32_t* max_len, void* workspace,
+                 size_t workspace_bytes, setok_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -312,6 +312,54 @@ def golden_detok(ns):
     _save("detok", **save)
 
 
+def golden_splice():
+    """prepare_inputs_labels_for_multimodal (setokim_arch.py:213-354), the reference's own function object, on a stub self."""
+    import types
+    fn = ref_loader.load_reference_splice()
+    g = torch.Generator().manual_seed(51)
+    V, H, B, L = 50, 16, 5, 12
+    emb = torch.nn.Embedding(V, H)
+    emb.weight.data = torch.randn(V, H, generator=g)
+    K = [3, 1, 4, 2, 5, 2]
+    feats = [torch.randn(k, H, generator=g) for k in K]
+    ids = torch.randint(0, V, (B, L), generator=g)
+    am = torch.ones(B, L, dtype=torch.long)
+    ids[0, 2] = -200                                    # one image
+    ids[1, 0] = -200; ids[1, 7] = -200                  # two images, one at the very start
+    am[1, 9:] = 0                                       # right-padded text
+    # sample 2: no placeholder -> still consumes one image index (:262-269)
+    ids[3, 11] = -200; am[3, :3] = 0                    # left-padded text, image at the very end
+    ids[4, 5] = -200; am[4, 6] = 0                      # a masked hole in the middle
+    labels = ids.clone()
+    labels[labels == -200] = -100
+    labels[0, 5] = -300                                 # TARGET_TOKEN_INDEX -> IGNORE (:345)
+    out = dict(V=np.array(V), H=np.array(H), embed=emb.weight.data.clone(), input_ids=ids, attention_mask=am, labels=labels,
+               feats=torch.cat(feats, 0), offsets=np.cumsum([0] + K).astype(np.int32))
+    cases = {"right": dict(side="right", maxlen=None, with_labels=True, with_mask=True),
+             "left": dict(side="left", maxlen=None, with_labels=True, with_mask=True),
+             "trunc": dict(side="right", maxlen=13, with_labels=True, with_mask=True),
+             "nolabels_nomask": dict(side="right", maxlen=None, with_labels=False, with_mask=False)}
+    for name, c in cases.items():
+        cfg = types.SimpleNamespace(tokenizer_padding_side=c["side"])
+        if c["maxlen"] is not None:
+            cfg.tokenizer_model_max_length = c["maxlen"]
+        model = types.SimpleNamespace(embed_tokens=emb)
+        me = types.SimpleNamespace(get_vision_tower=lambda: object(), encode_images=lambda images: feats, get_model=lambda: model, config=cfg,
+                                   device=torch.device("cpu"))
+        pos_in = torch.arange(L)[None].expand(B, L)
+        with torch.no_grad():
+            r = fn(me, ids.clone(), pos_in, am.clone() if c["with_mask"] else None, None, labels.clone() if c["with_labels"] else None,
+                   torch.zeros(len(K), 3, 4, 4))
+        _, pos, mask, _, embeds, lab = r
+        out[name + "/embeds"] = embeds
+        out[name + "/pos"] = pos
+        out[name + "/mask"] = mask if mask is not None else np.zeros(0)
+        out[name + "/labels"] = lab if lab is not None else np.zeros(0)
+        out[name + "/cfg"] = np.array([1 if c["side"] == "left" else 0, c["maxlen"] or 0, int(c["with_labels"]), int(c["with_mask"])])
+    out["names"] = np.array(list(cases.keys()))
+    _save("splice", **out)
+
+
 def main():
     if not ref_loader.available():
         raise SystemExit("reference tree not present: goldens can only be generated in the build container")
@@ -323,6 +371,7 @@ def main():
     golden_tower_and_e2e(ns)
     golden_projectors(ns)
     golden_detok(ns)
+    golden_splice()
 
 
 if __name__ == "__main__":

@@ -140,3 +140,42 @@ def build_reference_tokenizer(ns, hf_tower, *, hidden_dim, token_feat_dim, min_c
     tok.image_feature_encoder = tower
     tok.eval()
     return tok
+
+
+def load_reference_splice():
+    """The reference's `SetokimMetaForCausalLM.prepare_inputs_labels_for_multimodal` function object, from the unmodified
+    `src/model/setokim_arch.py`.  The module's imports of sibling builders / the diffusion loss / `src.constants` are
+    satisfied by stand-in modules (only the three token constants are real: they are read from `src/constants.py`)."""
+    if not available():
+        raise RuntimeError(f"reference tree not found under {REFERENCE_ROOT}")
+    pkg = "_setok_reference_model"
+    if pkg + ".setokim_arch" in sys.modules:
+        return sys.modules[pkg + ".setokim_arch"].SetokimMetaForCausalLM.prepare_inputs_labels_for_multimodal
+
+    def mk(name, **attrs):
+        m = types.ModuleType(name)
+        m.__spec__ = importlib.machinery.ModuleSpec(name, loader=None, is_package=True)
+        m.__path__ = []
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules[name] = m
+        return m
+
+    consts = {}
+    exec(open(os.path.join(REFERENCE_ROOT, "src/constants.py")).read(), consts)
+    stub = lambda *a, **k: None
+    mk(pkg)
+    mk(pkg + ".multimodal_encoder"); mk(pkg + ".multimodal_encoder.builder", build_vision_tower=stub)
+    mk(pkg + ".multimodal_projector"); mk(pkg + ".multimodal_projector.builder", build_vision_projector=stub)
+    mk(pkg + ".multimodal_generator"); mk(pkg + ".multimodal_generator.builder", build_vision_generator=stub)
+    mk(pkg + ".loss", DiffLoss=object)
+    had_src = "src" in sys.modules
+    if not had_src:
+        mk("src")
+    mk("src.constants", **{k: v for k, v in consts.items() if k.isupper()})
+    path = os.path.join(REFERENCE_ROOT, "src/model/setokim_arch.py")
+    spec = importlib.util.spec_from_file_location(pkg + ".setokim_arch", path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[pkg + ".setokim_arch"] = mod
+    spec.loader.exec_module(mod)
+    return mod.SetokimMetaForCausalLM.prepare_inputs_labels_for_multimodal

@@ -7,6 +7,7 @@ from .builder import build_vision_projector, build_vision_tower, encode_images  
 from .ragged import RaggedTokens  # noqa: F401
 from .tokenizer import CLIPVisionTower, SetokTokenizer  # noqa: F401
 from .detokenizer import SetokDeTokenizer  # noqa: F401
+from .splice import prepare_inputs_labels_for_multimodal  # noqa: F401
 
 __all__ = ["SetokTokenizer", "SetokDeTokenizer", "CLIPVisionTower", "RaggedTokens", "build_vision_tower", "build_vision_projector",
-           "encode_images", "SetokError"]
+           "encode_images", "prepare_inputs_labels_for_multimodal", "SetokError"]
