@@ -262,6 +262,18 @@ int setok_detok_forward(const setok_detok* detok, const void* tokens, int token_
  *   workspace      setok_splice_workspace_bytes(B, L, out_cap)
  */
 size_t setok_splice_workspace_bytes(int B, int L, int out_cap);
+/* Two-phase form for exactly-sized outputs: _plan computes lens / max_len (device) and leaves the plan in the workspace;
+ * the caller reads max_len once, allocates [B, max_len, ...] outputs and calls _fill with out_cap = max_len and the SAME
+ * workspace (sized for that out_cap).  out_cap_limit: truncate to this many columns at most (use a large value for none). */
+int setok_splice_plan(const int64_t* input_ids, const uint8_t* attention_mask, int B, int L, const int32_t* image_offsets,
+                      int n_images, int max_length, int out_cap_limit, int32_t* lens, int32_t* max_len, void* workspace,
+                      size_t workspace_bytes, setok_stream_t stream);
+int setok_splice_fill(const int64_t* input_ids, const uint8_t* attention_mask, const int64_t* labels, int B, int L,
+                      const void* embed, int dtype, int V, int H, const void* image_rows, const int32_t* image_offsets,
+                      int n_images, int pad_left, int out_cap, const int32_t* lens, const int32_t* max_len, void* embeds,
+                      int64_t* labels_out, uint8_t* mask_out, int64_t* pos_out, void* workspace, size_t workspace_bytes,
+                      setok_stream_t stream);
+/* Both phases in one call, for a caller with a known column bound (no host read). */
 int setok_splice(const int64_t* input_ids, const uint8_t* attention_mask, const int64_t* labels, int B, int L,
                  const void* embed, int dtype, int V, int H, const void* image_rows, const int32_t* image_offsets,
                  int n_images, int max_length, int pad_left, int out_cap, void* embeds, int64_t* labels_out,

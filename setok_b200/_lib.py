@@ -94,6 +94,9 @@ SIGNATURES = {
     "setok_detok_workspace_bytes": (c_size_t, [C.POINTER(Detok), c_int, c_int]),
     "setok_detok_forward": (c_int, [C.POINTER(Detok), c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "setok_splice_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "setok_splice_plan": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "setok_splice_fill": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "setok_splice": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "setok_project_workspace_bytes": (c_size_t, [C.POINTER(Projector), c_int]),

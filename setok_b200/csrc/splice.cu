@@ -153,44 +153,76 @@ using namespace setok;
 extern "C" size_t setok_splice_workspace_bytes(int B, int L, int out_cap) {
   if (B <= 0 || L <= 0 || out_cap <= 0) return 0;
   Arena a(nullptr, 0);
-  a.take<int32_t>(B); a.take<int32_t>(B); a.take<int32_t>(B);
+  a.take<int32_t>(B); a.take<int32_t>(B); a.take<int32_t>(B);      // the plan lives in the first three slices: the same for any out_cap
   a.take<int32_t>(static_cast<size_t>(B) * out_cap);
   return a.off;
 }
 
-extern "C" int setok_splice(const int64_t* input_ids, const uint8_t* attention_mask, const int64_t* labels, int B, int L, const void* embed,
-                            int dtype, int V, int H, const void* image_rows, const int32_t* image_offsets, int n_images, int max_length,
-                            int pad_left, int out_cap, void* embeds, int64_t* labels_out, uint8_t* mask_out, int64_t* pos_out, int32_t* lens,
-                            int32_t* max_len, void* workspace, size_t workspace_bytes, setok_stream_t stream_) {
+namespace {
+struct SpliceWs { int32_t *n_valid, *n_img, *img_start, *src; };
+void splice_carve(int B, int out_cap, Arena& a, SpliceWs* w) {
+  w->n_valid = a.take<int32_t>(B); w->n_img = a.take<int32_t>(B); w->img_start = a.take<int32_t>(B);
+  w->src = a.take<int32_t>(static_cast<size_t>(B) * out_cap);
+}
+}  // namespace
+
+// Phase 1: lengths only (lens, max_len on the device).  A caller that wants exactly-sized outputs reads max_len once and
+// passes it to setok_splice_fill as out_cap; the workspace carries the plan between the two calls.
+extern "C" int setok_splice_plan(const int64_t* input_ids, const uint8_t* attention_mask, int B, int L, const int32_t* image_offsets, int n_images,
+                                 int max_length, int out_cap_limit, int32_t* lens, int32_t* max_len, void* workspace, size_t workspace_bytes,
+                                 setok_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SETOK_REQUIRE(input_ids && image_offsets && lens && max_len, SETOK_ERR_BAD_ARG, "splice_plan: null pointer");
+  SETOK_REQUIRE(B > 0 && L > 0 && n_images >= 0 && out_cap_limit > 0, SETOK_ERR_BAD_ARG, "splice_plan: bad shape B=%d L=%d", B, L);
+  SETOK_REQUIRE(workspace && workspace_bytes >= setok_splice_workspace_bytes(B, L, 1), SETOK_ERR_WORKSPACE, "splice_plan: workspace too small");
+  Arena a(workspace, workspace_bytes);
+  SpliceWs w;
+  splice_carve(B, 1, a, &w);
+  splice_count_kernel<<<B, SP_THREADS, 0, stream>>>(input_ids, attention_mask, L, w.n_valid, w.n_img);
+  SETOK_LAUNCH_CHECK();
+  splice_plan_kernel<<<1, 32, 0, stream>>>(w.n_valid, w.n_img, image_offsets, n_images, B, max_length, out_cap_limit, w.img_start, lens, max_len);
+  SETOK_LAUNCH_CHECK();
+  return SETOK_OK;
+}
+
+// Phase 2: descriptors + row gather into outputs of out_cap columns (lens / max_len / workspace from setok_splice_plan).
+extern "C" int setok_splice_fill(const int64_t* input_ids, const uint8_t* attention_mask, const int64_t* labels, int B, int L, const void* embed,
+                                 int dtype, int V, int H, const void* image_rows, const int32_t* image_offsets, int n_images, int pad_left,
+                                 int out_cap, const int32_t* lens, const int32_t* max_len, void* embeds, int64_t* labels_out, uint8_t* mask_out,
+                                 int64_t* pos_out, void* workspace, size_t workspace_bytes, setok_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SETOK_REQUIRE(input_ids && embed && image_rows && image_offsets && embeds && labels_out && mask_out && pos_out && lens && max_len,
-                SETOK_ERR_BAD_ARG, "splice: null pointer");
-  SETOK_REQUIRE(B > 0 && L > 0 && V > 0 && H > 0 && n_images >= 0 && out_cap > 0, SETOK_ERR_BAD_ARG, "splice: bad shape B=%d L=%d V=%d H=%d out_cap=%d", B, L, V, H, out_cap);
-  SETOK_REQUIRE(dtype == SETOK_F32 || dtype == SETOK_BF16, SETOK_ERR_BAD_ARG, "splice: bad dtype %d", dtype);
+                SETOK_ERR_BAD_ARG, "splice_fill: null pointer");
+  SETOK_REQUIRE(B > 0 && L > 0 && V > 0 && H > 0 && n_images >= 0 && out_cap > 0, SETOK_ERR_BAD_ARG, "splice_fill: bad shape B=%d L=%d V=%d H=%d out_cap=%d", B, L, V, H, out_cap);
+  SETOK_REQUIRE(dtype == SETOK_F32 || dtype == SETOK_BF16, SETOK_ERR_BAD_ARG, "splice_fill: bad dtype %d", dtype);
   const int esz = dtype == SETOK_F32 ? 4 : 2;
   SETOK_REQUIRE((H * esz) % 16 == 0 && aligned16(embed) && aligned16(image_rows) && aligned16(embeds), SETOK_ERR_UNSUPPORTED,
-                "splice: rows must be 16-byte multiples and 16-byte aligned (H=%d)", H);
-  SETOK_REQUIRE(workspace && workspace_bytes >= setok_splice_workspace_bytes(B, L, out_cap), SETOK_ERR_WORKSPACE, "splice: workspace too small");
+                "splice_fill: rows must be 16-byte multiples and 16-byte aligned (H=%d)", H);
+  SETOK_REQUIRE(workspace && workspace_bytes >= setok_splice_workspace_bytes(B, L, out_cap), SETOK_ERR_WORKSPACE, "splice_fill: workspace too small");
   Arena a(workspace, workspace_bytes);
-  int32_t* n_valid = a.take<int32_t>(B);
-  int32_t* n_img = a.take<int32_t>(B);
-  int32_t* img_start = a.take<int32_t>(B);
-  int32_t* src = a.take<int32_t>(static_cast<size_t>(B) * out_cap);
-  splice_count_kernel<<<B, SP_THREADS, 0, stream>>>(input_ids, attention_mask, L, n_valid, n_img);
-  SETOK_LAUNCH_CHECK();
-  splice_plan_kernel<<<1, 32, 0, stream>>>(n_valid, n_img, image_offsets, n_images, B, max_length, out_cap, img_start, lens, max_len);
-  SETOK_LAUNCH_CHECK();
-  splice_fill_kernel<<<B, SP_THREADS, 0, stream>>>(input_ids, attention_mask, labels, L, V, image_offsets, n_images, img_start, lens, max_len,
-                                                   pad_left, out_cap, labels_out, mask_out, pos_out, src);
+  SpliceWs w;
+  splice_carve(B, out_cap, a, &w);
+  splice_fill_kernel<<<B, SP_THREADS, 0, stream>>>(input_ids, attention_mask, labels, L, V, image_offsets, n_images, w.img_start, lens, max_len,
+                                                   pad_left, out_cap, labels_out, mask_out, pos_out, w.src);
   SETOK_LAUNCH_CHECK();
   const long long rows = static_cast<long long>(B) * out_cap;
   const long long vecs = rows * (H * esz / 16);
   long long blocks = (vecs + 255) / 256;
   if (blocks > num_sms() * 16LL) blocks = num_sms() * 16LL;
   if (dtype == SETOK_F32)
-    splice_gather_kernel<float><<<static_cast<int>(blocks), 256, 0, stream>>>(src, static_cast<const float*>(embed), static_cast<const float*>(image_rows), H, rows, static_cast<float*>(embeds));
+    splice_gather_kernel<float><<<static_cast<int>(blocks), 256, 0, stream>>>(w.src, static_cast<const float*>(embed), static_cast<const float*>(image_rows), H, rows, static_cast<float*>(embeds));
   else
-    splice_gather_kernel<bf16><<<static_cast<int>(blocks), 256, 0, stream>>>(src, static_cast<const bf16*>(embed), static_cast<const bf16*>(image_rows), H, rows, static_cast<bf16*>(embeds));
+    splice_gather_kernel<bf16><<<static_cast<int>(blocks), 256, 0, stream>>>(w.src, static_cast<const bf16*>(embed), static_cast<const bf16*>(image_rows), H, rows, static_cast<bf16*>(embeds));
   SETOK_LAUNCH_CHECK();
   return SETOK_OK;
+}
+
+// Both phases back to back for a caller with a known column bound (e.g. tokenizer_model_max_length): no host read at all.
+extern "C" int setok_splice(const int64_t* input_ids, const uint8_t* attention_mask, const int64_t* labels, int B, int L, const void* embed,
+                            int dtype, int V, int H, const void* image_rows, const int32_t* image_offsets, int n_images, int max_length,
+                            int pad_left, int out_cap, void* embeds, int64_t* labels_out, uint8_t* mask_out, int64_t* pos_out, int32_t* lens,
+                            int32_t* max_len, void* workspace, size_t workspace_bytes, setok_stream_t stream) {
+  SETOK_TRY(setok_splice_plan(input_ids, attention_mask, B, L, image_offsets, n_images, max_length, out_cap, lens, max_len, workspace, workspace_bytes, stream));
+  return setok_splice_fill(input_ids, attention_mask, labels, B, L, embed, dtype, V, H, image_rows, image_offsets, n_images, pad_left, out_cap, lens,
+                           max_len, embeds, labels_out, mask_out, pos_out, workspace, workspace_bytes, stream);
 }

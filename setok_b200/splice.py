@@ -48,26 +48,28 @@ def prepare_inputs_labels_for_multimodal(input_ids: torch.Tensor, position_ids: 
     V, H = weight.shape
     mask8 = None if attention_mask is None else attention_mask.to(dev).bool().to(torch.uint8).contiguous()
     lab = None if labels is None else labels.to(device=dev, dtype=torch.int64).contiguous()
-    # capacity: every placeholder replaced by its image's rows cannot exceed L + all image rows; the true maximum is read back once
-    cap = L + int(rows.shape[0])
-    if tokenizer_model_max_length is not None:
-        cap = min(cap, int(tokenizer_model_max_length))
-    cap = max(cap, 1)
-    embeds = torch.empty(B, cap, H, dtype=dtype, device=dev)
-    labels_out = torch.empty(B, cap, dtype=torch.int64, device=dev)
-    mask_out = torch.empty(B, cap, dtype=torch.uint8, device=dev)
-    pos_out = torch.empty(B, cap, dtype=torch.int64, device=dev)
     lens = torch.empty(B, dtype=torch.int32, device=dev)
     max_len = torch.empty(1, dtype=torch.int32, device=dev)
     lib = _lib.load()
-    ws = ops.workspace(dev, lib.setok_splice_workspace_bytes(B, L, cap), "splice")
+    limit = int(tokenizer_model_max_length) if tokenizer_model_max_length is not None else 2 ** 30
+    # one workspace for both phases (the plan lives in its first slices): sized for the column upper bound L + all image rows,
+    # which costs 4 bytes per column
+    ws = ops.workspace(dev, lib.setok_splice_workspace_bytes(B, L, L + int(rows.shape[0])), "splice")
     with torch.cuda.device(dev):
-        st = lib.setok_splice(ids.data_ptr(), ops._p(mask8), ops._p(lab), B, L, weight.data_ptr(), ops._dt(weight), V, H, rows.data_ptr(),
-                              offsets.data_ptr(), n_images, int(tokenizer_model_max_length or 0), int(tokenizer_padding_side == "left"), cap,
-                              embeds.data_ptr(), labels_out.data_ptr(), mask_out.data_ptr(), pos_out.data_ptr(), lens.data_ptr(),
-                              max_len.data_ptr(), ws.data_ptr(), ws.numel(), ops._stream(dev))
-    _lib.check(st, "setok_splice")
-    T = int(max_len.item())                                    # the one host read: the reference's max(x.shape[0] ...) (:313)
+        st = lib.setok_splice_plan(ids.data_ptr(), ops._p(mask8), B, L, offsets.data_ptr(), n_images, int(tokenizer_model_max_length or 0), limit,
+                                   lens.data_ptr(), max_len.data_ptr(), ws.data_ptr(), ws.numel(), ops._stream(dev))
+    _lib.check(st, "setok_splice_plan")
+    T = max(int(max_len.item()), 1)                            # the one host read: the reference's max(x.shape[0] ...) (:313)
+    embeds = torch.empty(B, T, H, dtype=dtype, device=dev)
+    labels_out = torch.empty(B, T, dtype=torch.int64, device=dev)
+    mask_out = torch.empty(B, T, dtype=torch.uint8, device=dev)
+    pos_out = torch.empty(B, T, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        st = lib.setok_splice_fill(ids.data_ptr(), ops._p(mask8), ops._p(lab), B, L, weight.data_ptr(), ops._dt(weight), V, H, rows.data_ptr(),
+                                   offsets.data_ptr(), n_images, int(tokenizer_padding_side == "left"), T, lens.data_ptr(), max_len.data_ptr(),
+                                   embeds.data_ptr(), labels_out.data_ptr(), mask_out.data_ptr(), pos_out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                   ops._stream(dev))
+    _lib.check(st, "setok_splice_fill")
     new_input_embeds = embeds[:, :T]
     new_labels = None if labels is None else labels_out[:, :T]
     new_mask = None if attention_mask is None else mask_out[:, :T].to(attention_mask.dtype)

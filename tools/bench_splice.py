@@ -34,7 +34,6 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
 T = out[4].shape[1]
-cap = L + rows.shape[0]
-moved = (float(mask.sum()) - B + float(K.sum())) * H * 2 + B * cap * H * 2      # rows gathered + the capacity-sized output written
-print(f"splice B={B} L={L} H={H} bf16: {ms * 1e3:.1f} us per call (incl. the one host read of max_len), T={T}, capacity {cap} columns; "
+moved = (float(mask.sum()) - B + float(K.sum())) * H * 2 + B * T * H * 2       # rows gathered + the (B, T, H) output written
+print(f"splice B={B} L={L} H={H} bf16: {ms * 1e3:.1f} us per call (two phases incl. the one host read of max_len), T={T}; "
       f"{moved / ms / 1e6:.0f} GB/s over {moved / 1e6:.0f} MB moved")
