@@ -31,7 +31,7 @@ typedef enum {
   SETOK_ERR_WORKSPACE = -4     /* workspace smaller than the matching *_workspace_bytes() query  */
 } setok_status;
 
-typedef enum { SETOK_F32 = 0, SETOK_BF16 = 1 } setok_dtype;
+typedef enum { SETOK_F32 = 0, SETOK_BF16 = 1, SETOK_U8 = 2 /* images only: setok_vit_forward_u8 */ } setok_dtype;
 typedef enum { SETOK_ACT_NONE = 0, SETOK_ACT_QUICK_GELU = 1, SETOK_ACT_GELU_ERF = 2 } setok_act;
 
 const char* setok_last_error(void);
@@ -115,6 +115,17 @@ size_t setok_vit_workspace_bytes(const setok_vit* vit, int B);
 int setok_vit_forward(const setok_vit* vit, const void* images, int image_dtype, int B, int n_layers_run,
                       int keep_cls, void* features, int feature_dtype, void* workspace, size_t workspace_bytes,
                       setok_stream_t stream);
+
+/* SURVEY 8f row 3 (normalisation part): uint8 pixels straight into the patch embedding.  images (device) uint8 [B,3,H,W]
+ * (channels first, already at the tower's resolution); the CLIPImageProcessor arithmetic of transformers 4.46.3 --
+ * rescale: float32(float64(u8) * rescale_factor), normalize: (x - mean) / std in float32 -- is applied inside the im2col
+ * pass, so the host->device copy carries 1 byte per pixel instead of 4.  lut[v] = float32(v * rescale_factor) is built by
+ * the caller in double precision (256 entries).  pos_table may be NULL (then features = hidden_states[...][:, 1:] in
+ * feature_dtype) or the (N, C) sincos table (then the output is the f32 position-embedded tensor, as setok_vit_forward_pos). */
+typedef struct { float lut[256]; float mean[3]; float std[3]; } setok_u8_norm;
+int setok_vit_forward_u8(const setok_vit* vit, const uint8_t* images, const setok_u8_norm* norm, int B, int n_layers_run,
+                         int keep_cls, const float* pos_table, void* features, int feature_dtype, void* workspace,
+                         size_t workspace_bytes, setok_stream_t stream);
 
 /* Same tower, with feature_select('patch') and the position-embedding add of tokenizer.py:164-169 fused into the last
  * row pass: x_pos (device) f32 [B, N, C] = hidden_states[n_layers_run][:, 1:] + pos_table.  pos_table: (N, C) f32

@@ -51,6 +51,10 @@ class Projector(C.Structure):
                 ("norm_g", c_void_p), ("norm_b", c_void_p)]
 
 
+class U8Norm(C.Structure):
+    _fields_ = [("lut", c_float * 256), ("mean", c_float * 3), ("std", c_float * 3)]
+
+
 class QFormerLayer(C.Structure):
     _fields_ = [("w_qkv", c_void_p), ("b_qkv", c_void_p), ("w_so", c_void_p), ("b_so", c_void_p), ("ln_s_g", c_void_p), ("ln_s_b", c_void_p),
                 ("has_cross", c_int), ("w_cq", c_void_p), ("b_cq", c_void_p), ("w_ckv", c_void_p), ("b_ckv", c_void_p), ("w_co", c_void_p),
@@ -80,6 +84,7 @@ SIGNATURES = {
     "setok_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "setok_vit_workspace_bytes": (c_size_t, [C.POINTER(Vit), c_int]),
     "setok_vit_forward": (c_int, [C.POINTER(Vit), c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    "setok_vit_forward_u8": (c_int, [C.POINTER(Vit), c_void_p, C.POINTER(U8Norm), c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "setok_vit_forward_pos": (c_int, [C.POINTER(Vit), c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "setok_dpc_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "setok_dpc_cluster_embedded": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p,

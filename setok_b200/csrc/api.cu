@@ -135,7 +135,8 @@ extern "C" size_t setok_vit_workspace_bytes(const setok_vit* vit, int B) {
 
 namespace {
 int vit_forward_impl(const setok_vit* v, const void* images, int image_dtype, int B, int n_layers_run, int keep_cls, void* features,
-                     int feature_dtype, const float* pos_add, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                     int feature_dtype, const float* pos_add, void* workspace, size_t workspace_bytes, cudaStream_t stream,
+                     const setok_u8_norm* u8norm = nullptr) {
   SETOK_TRY(check_vit(v));
   SETOK_REQUIRE(images && features && B > 0, SETOK_ERR_BAD_ARG, "vit_forward: null images/features or B <= 0");
   SETOK_REQUIRE(n_layers_run >= 0 && n_layers_run <= v->layers, SETOK_ERR_BAD_ARG, "vit_forward: n_layers_run %d outside [0, %d]", n_layers_run, v->layers);
@@ -149,7 +150,12 @@ int vit_forward_impl(const setok_vit* v, const void* images, int image_dtype, in
 
   // embeddings (modeling_clip.py:199-220): conv patch-embed as im2col + GEMM whose epilogue scatters the
   // rows past each image's CLS slot and adds the position embedding; CLS rows; pre_layrnorm.
-  SETOK_TRY(launch_im2col(images, image_dtype, w.A, B, v->image_size, v->image_size, v->patch, Kp, stream));
+  if (image_dtype == SETOK_U8) {
+    SETOK_REQUIRE(u8norm != nullptr, SETOK_ERR_BAD_ARG, "vit_forward: uint8 images need the normalisation constants (setok_vit_forward_u8)");
+    SETOK_TRY(launch_im2col_u8(static_cast<const uint8_t*>(images), u8norm, w.A, B, v->image_size, v->image_size, v->patch, Kp, stream));
+  } else {
+    SETOK_TRY(launch_im2col(images, image_dtype, w.A, B, v->image_size, v->image_size, v->patch, Kp, stream));
+  }
   SETOK_TRY(launch_gemm(GemmArgs{w.A, Kp, v->w_patch, Kp, w.emb, C, SETOK_F32, nullptr, v->pos, C, SETOK_F32, SETOK_ACT_NONE, B * P, C, Kp, nullptr, P}, stream));
   SETOK_TRY(launch_cls_rows(w.emb, v->cls, v->pos, B, T, C, stream));
   SETOK_TRY(launch_layernorm(w.emb, SETOK_F32, w.x, SETOK_BF16, v->pre_ln_g, v->pre_ln_b, v->ln_eps, R, C, nullptr, nullptr, stream));
@@ -170,6 +176,17 @@ extern "C" int setok_vit_forward(const setok_vit* v, const void* images, int ima
                                  void* features, int feature_dtype, void* workspace, size_t workspace_bytes, setok_stream_t stream) {
   return vit_forward_impl(v, images, image_dtype, B, n_layers_run, keep_cls, features, feature_dtype, nullptr, workspace, workspace_bytes,
                           static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int setok_vit_forward_u8(const setok_vit* v, const uint8_t* images, const setok_u8_norm* norm, int B, int n_layers_run, int keep_cls,
+                                    const float* pos_table, void* features, int feature_dtype, void* workspace, size_t workspace_bytes,
+                                    setok_stream_t stream) {
+  SETOK_REQUIRE(norm != nullptr, SETOK_ERR_BAD_ARG, "vit_forward_u8: null normalisation constants");
+  for (int c = 0; c < 3; ++c) SETOK_REQUIRE(norm->std[c] != 0.f, SETOK_ERR_BAD_ARG, "vit_forward_u8: std[%d] is zero", c);
+  SETOK_REQUIRE(pos_table == nullptr || (keep_cls == 0 && feature_dtype == SETOK_F32 && aligned16(pos_table)), SETOK_ERR_BAD_ARG,
+                "vit_forward_u8: the fused position-embedding add needs 'patch' features in f32 and a 16-byte aligned table");
+  return vit_forward_impl(v, images, SETOK_U8, B, n_layers_run, keep_cls, features, feature_dtype, pos_table, workspace, workspace_bytes,
+                          static_cast<cudaStream_t>(stream), norm);
 }
 
 extern "C" int setok_vit_forward_pos(const setok_vit* v, const void* images, int image_dtype, int B, int n_layers_run, const float* pos_table,

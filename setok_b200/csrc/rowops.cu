@@ -137,6 +137,40 @@ __global__ void __launch_bounds__(256) im2col_kernel(const TI* __restrict__ img,
   }
 }
 
+// uint8 pixels: CLIPImageProcessor's rescale + normalize (transformers 4.46.3, numpy float32 arithmetic) fused into the im2col
+//   x = lut[u8] (= float32(float64(u8) * rescale_factor), built on the host);  y = (x - mean[c]) / std[c], rounded separately
+__global__ void __launch_bounds__(256) im2col_u8_kernel(const uint8_t* __restrict__ img, bf16* __restrict__ A, int B, int H, int W, int patch,
+                                                        int Kp, const setok_u8_norm nrm) {
+  __shared__ float lut[256];
+  lut[threadIdx.x] = nrm.lut[threadIdx.x];
+  __syncthreads();
+  const int gw = W / patch, gh = H / patch;
+  const int K = 3 * patch * patch;
+  const long long total = static_cast<long long>(B) * gh * gw * (Kp / 2);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cp = static_cast<int>(i % (Kp / 2));
+    const long long row = i / (Kp / 2);
+    const int px = static_cast<int>(row % gw);
+    const int py = static_cast<int>((row / gw) % gh);
+    const int b = static_cast<int>(row / (static_cast<long long>(gw) * gh));
+    float v[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int col = cp * 2 + e;
+      v[e] = 0.f;
+      if (col < K) {
+        const int c = col / (patch * patch);
+        const int rem = col % (patch * patch);
+        const int ky = rem / patch, kx = rem % patch;
+        const uint8_t u = img[((static_cast<long long>(b) * 3 + c) * H + (py * patch + ky)) * W + (px * patch + kx)];
+        v[e] = __fdiv_rn(__fsub_rn(lut[u], nrm.mean[c]), nrm.std[c]);
+      }
+    }
+    *reinterpret_cast<uint32_t*>(A + row * Kp + cp * 2) = pack_bf16x2(v[0], v[1]);
+  }
+}
+
 // emb[b*T + 0, :] = cls + pos[0]   (fp32)
 __global__ void cls_rows_kernel(float* __restrict__ emb, const float* __restrict__ cls, const float* __restrict__ pos,
                                 int B, int T, int C) {
@@ -340,6 +374,13 @@ int launch_im2col(const void* images, int image_dtype, void* A, int B, int H, in
   if (image_dtype == SETOK_F32) im2col_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(images), static_cast<bf16*>(A), B, H, W, patch, Kp);
   else if (image_dtype == SETOK_BF16) im2col_kernel<bf16><<<grid, 256, 0, stream>>>(static_cast<const bf16*>(images), static_cast<bf16*>(A), B, H, W, patch, Kp);
   else return fail(SETOK_ERR_BAD_ARG, "im2col: bad image dtype %d", image_dtype);
+  SETOK_LAUNCH_CHECK();
+  return SETOK_OK;
+}
+
+int launch_im2col_u8(const uint8_t* images, const setok_u8_norm* norm, void* A, int B, int H, int W, int patch, int Kp, cudaStream_t stream) {
+  const long long total = static_cast<long long>(B) * (H / patch) * (W / patch) * (Kp / 2);
+  im2col_u8_kernel<<<grid_for(total, 256, 16), 256, 0, stream>>>(images, static_cast<bf16*>(A), B, H, W, patch, Kp, *norm);
   SETOK_LAUNCH_CHECK();
   return SETOK_OK;
 }

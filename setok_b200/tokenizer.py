@@ -251,6 +251,22 @@ class CLIPVisionTower(nn.Module):
             self._resized[size] = hit
         return hit[0]
 
+    def u8_norm(self) -> "_lib.U8Norm":
+        """Constants of the tower's image processor for the uint8 path (CLIPImageProcessor.rescale / .normalize of
+        transformers 4.46.3): lut[v] = float32(float64(v) * rescale_factor), float32 mean / std."""
+        ip = self.image_processor
+        mean = list(getattr(ip, "image_mean", None) or (0.48145466, 0.4578275, 0.40821073))
+        std = list(getattr(ip, "image_std", None) or (0.26862954, 0.26130258, 0.27577711))
+        rescale = float(getattr(ip, "rescale_factor", None) or 1.0 / 255.0)
+        n = _lib.U8Norm()
+        lut = (np.arange(256, dtype=np.float64) * rescale).astype(np.float32)
+        for v in range(256):
+            n.lut[v] = float(lut[v])
+        for c in range(3):
+            n.mean[c] = float(np.float32(mean[c]))
+            n.std[c] = float(np.float32(std[c]))
+        return n
+
     def layers_to_run(self) -> int:
         L = self.config.num_hidden_layers
         idx = self.select_layer if self.select_layer >= 0 else L + 1 + self.select_layer
@@ -280,7 +296,10 @@ class CLIPVisionTower(nn.Module):
             vit = self._vit_for_size(int(images.shape[2]))
         out_dtype = images.dtype
         x = images.to(device=dev)
-        if x.dtype not in (torch.float32, torch.bfloat16):
+        is_u8 = x.dtype == torch.uint8
+        if is_u8:
+            out_dtype = torch.float32       # raw pixels: the processor's float32 output dtype (mm_utils.py:166-182)
+        elif x.dtype not in (torch.float32, torch.bfloat16):
             x = x.to(torch.float32)
         x = x.contiguous()
         B = x.shape[0]
@@ -290,6 +309,22 @@ class CLIPVisionTower(nn.Module):
         lib = _lib.load()
         nbytes = lib.setok_vit_workspace_bytes(C.byref(vit), B)
         ws = ops.workspace(dev, nbytes, "vit")
+        if is_u8:
+            # uint8 pixels (B, 3, H, W) already at the tower's resolution: rescale + normalize run inside the patch-embedding
+            # im2col with the processor's constants, so the upload is 1 byte per pixel
+            if pos_embedding is not None and keep_cls:
+                raise SetokError("the fused position-embedding add needs mm_vision_select_feature='patch'")
+            norm = self.u8_norm()
+            pos = None
+            if pos_embedding is not None:
+                g = vit.image_size // vit.patch
+                pos = pos_embedding.table(g, g, dev)
+            feats = torch.empty(B, N, vit.hidden, dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                st = lib.setok_vit_forward_u8(C.byref(vit), x.data_ptr(), C.byref(norm), B, self.layers_to_run(), keep_cls, ops._p(pos),
+                                              feats.data_ptr(), ops._dt(feats), ws.data_ptr(), ws.numel(), ops._stream(dev))
+            _lib.check(st, "setok_vit_forward_u8")
+            return feats
         if pos_embedding is not None:
             if keep_cls:
                 raise SetokError("the fused position-embedding add needs mm_vision_select_feature='patch'")

@@ -383,3 +383,28 @@ def test_config5_mixed_resolution_ragged_batch():
             assert torch.equal(idxs[i].cpu()[firm], oidx[firm]), (i, s)
             if bool(firm.all()):
                 assert _err(rt[i], toks)[1] < 1e-2
+
+
+def test_tower_uint8_pixels_equal_the_float_path():
+    """setok_vit_forward_u8: uint8 pixels normalised inside the patch-embedding im2col give bit-identical features (and the
+    same tokens through SetokTokenizer.forward) as the float32 path fed with the processor-normalised images."""
+    import numpy as np
+    C, L, H, P, IMG, B = 128, 2, 2, 4, 32, 4
+    cfg = dict(hidden_size=C, intermediate_size=4 * C, num_hidden_layers=L, num_attention_heads=H, image_size=IMG, patch_size=P)
+    tok = _make_tokenizer(C, 64, 256, 8, 0.5, cfg, seed=8)
+    tower = tok.image_feature_encoder
+    u8 = torch.randint(0, 256, (B, 3, IMG, IMG), dtype=torch.uint8, generator=torch.Generator().manual_seed(9))
+    n = tower.u8_norm()
+    lut = torch.tensor(list(n.lut), dtype=torch.float32)
+    mean = torch.tensor(list(n.mean), dtype=torch.float32).view(1, 3, 1, 1)
+    std = torch.tensor(list(n.std), dtype=torch.float32).view(1, 3, 1, 1)
+    normalised = (lut[u8.long()] - mean) / std                                  # the processor's float32 output (tests/test_host_cpu.py)
+    f_u8 = tower(u8.to(DEV))
+    f_f32 = tower(normalised.to(DEV))
+    assert f_u8.dtype == torch.float32 and torch.equal(f_u8, f_f32)
+    noise = torch.rand(B, (IMG // P) ** 2, generator=torch.Generator().manual_seed(10)).to(DEV)
+    rt_u8, idx_u8, sc_u8 = tok(u8.to(DEV), k=8, noise=noise)
+    rt_f, idx_f, sc_f = tok(normalised.to(DEV), k=8, noise=noise)
+    assert torch.equal(idx_u8, idx_f) and torch.equal(sc_u8, sc_f) and torch.equal(rt_u8.offsets, rt_f.offsets)
+    n_tok = int(rt_f.offsets[-1])
+    assert torch.equal(rt_u8.data[:n_tok], rt_f.data[:n_tok])

@@ -92,3 +92,33 @@ def test_shard_batch_covers_everything_once():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
             assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+
+
+def test_u8_normalisation_constants_reproduce_the_hf_processor():
+    """The uint8 tower path (setok_vit_forward_u8) applies lut[u8] -> (x - mean) / std in float32 with separately rounded
+    steps.  Evaluated in numpy with the constants `CLIPVisionTower.u8_norm()` hands to the kernel, that arithmetic must
+    reproduce, bit for bit, `transformers.image_transforms.rescale` + `normalize` -- the numpy functions the reference's
+    pinned transformers==4.46.3 CLIPImageProcessor.preprocess calls (image_processing_clip.py: self.rescale / self.normalize).
+    The torchvision-backed processor class of the installed transformers 5.x fuses the two steps and lands within 1 ulp."""
+    import numpy as np
+    from transformers import CLIPImageProcessor
+    from transformers.image_transforms import normalize, rescale
+    from setok_b200 import CLIPVisionTower
+    cfg = dict(hidden_size=32, intermediate_size=64, num_hidden_layers=1, num_attention_heads=2, image_size=16, patch_size=4)
+    tower = CLIPVisionTower("siglip-synthetic", vision_config=cfg)
+    n = tower.u8_norm()
+    lut = np.array(list(n.lut), dtype=np.float32)
+    mean = np.array(list(n.mean), dtype=np.float32)
+    std = np.array(list(n.std), dtype=np.float32)
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, size=(3, 16, 16, 3), dtype=np.uint8)                 # HWC, as PIL / numpy images arrive
+    chw = np.transpose(img, (0, 3, 1, 2))
+    ours = (lut[chw] - mean[None, :, None, None]) / std[None, :, None, None]
+    assert ours.dtype == np.float32
+    ip = CLIPImageProcessor(do_resize=False, do_center_crop=False, do_convert_rgb=False)
+    for i in range(img.shape[0]):
+        x = rescale(img[i], scale=ip.rescale_factor, input_data_format="channels_last")
+        y = normalize(x, mean=ip.image_mean, std=ip.image_std, input_data_format="channels_last")
+        assert y.dtype == np.float32 and np.array_equal(ours[i], np.transpose(y, (2, 0, 1)))
+    fast = ip.preprocess(list(img), return_tensors="np", input_data_format="channels_last")["pixel_values"]
+    assert np.abs(ours - fast).max() <= 2.4e-7 * np.abs(fast).max()
