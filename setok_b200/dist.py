@@ -45,3 +45,18 @@ def shard_batch(n_items: int, rank: int, world: int):
     base, rem = divmod(n_items, world)
     start = rank * base + min(rank, rem)
     return start, start + base + (1 if rank < rem else 0)
+
+
+def deal_by_cost(sizes, world: int):
+    """Mixed-resolution batches (BASELINE config 5): the per-image cost grows like N^2 + 24 N C, so a contiguous split can
+    leave one rank with all the 448^2 images.  Longest-processing-time dealing: images sorted by cost, each goes to the
+    currently lightest rank.  `sizes` = per-image side length (or token count); returns `world` index lists whose
+    concatenation is a permutation of range(len(sizes))."""
+    order = sorted(range(len(sizes)), key=lambda i: (-float(sizes[i]) ** 2, i))
+    loads = [0.0] * world
+    out = [[] for _ in range(world)]
+    for i in order:
+        r = min(range(world), key=lambda j: (loads[j], j))
+        out[r].append(i)
+        loads[r] += float(sizes[i]) ** 2
+    return [sorted(o) for o in out]

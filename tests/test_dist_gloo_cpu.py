@@ -40,3 +40,16 @@ def test_all_gather_ragged_world2():
     for rank, counts, packed in res:
         assert counts == [2, 0, 5, 1, 4, 1]
         assert torch.equal(packed, torch.cat([exp0, exp1]))
+
+
+def test_deal_by_cost_balances_mixed_resolutions():
+    """BASELINE config 5: equal thirds of {224, 336, 448}^2 images over 8 ranks: every image is dealt exactly once and the
+    heaviest rank carries at most 1.2x the mean cost (a contiguous split would put all 448^2 images on three ranks)."""
+    from setok_b200.dist import deal_by_cost, shard_batch
+    sizes = [224] * 64 + [336] * 64 + [448] * 64
+    parts = deal_by_cost(sizes, 8)
+    assert sorted(i for p in parts for i in p) == list(range(len(sizes)))
+    cost = [sum(sizes[i] ** 2 for i in p) for p in parts]
+    assert max(cost) <= 1.2 * sum(cost) / 8
+    contiguous = [sum(s ** 2 for s in sizes[slice(*shard_batch(len(sizes), r, 8))]) for r in range(8)]
+    assert max(contiguous) > 1.5 * sum(contiguous) / 8
