@@ -101,12 +101,21 @@ typedef struct {
 typedef struct {
   int image_size, patch, hidden, heads, layers, mlp;
   float ln_eps;
-  const void* w_patch;   /* bf16 [C, Kp], Kp = round_up(3*patch*patch, 64), columns (c, ky, kx), zero padded */
+  const void* w_patch;   /* bf16 [C, Kp], Kp = round_up(3*patch*patch, 64), columns (c, ky, kx), zero padded;
+                            with SETOK_VIT_PATCH_SPLIT: bf16 [C, 3*Kp] = [w_hi | w_hi | w_lo], w = w_hi + w_lo */
   const float* cls;      /* f32 [C] */
   const float* pos;      /* f32 [(N+1), C] */
   const float* pre_ln_g; const float* pre_ln_b;
   const setok_vit_layer* layer;   /* host array of `layers` entries */
+  int flags;             /* SETOK_VIT_* bits; 0 = bf16 residual stream */
 } setok_vit;
+/* Residual stream x of the tower kept in f32 between layers (LayerNorm reads f32, the out_proj / fc2 epilogues add and
+ * store f32) instead of being rounded to bf16 after every residual add: 2 x layers fewer bf16 roundings of x. */
+#define SETOK_VIT_RESIDUAL_F32 1
+/* Patch embedding (modeling_clip.py:209) evaluated as a 3-term bf16 hi/lo split of pixels and weights in one GEMM of
+ * K = 3*Kp (pixel.w = hi.w_hi + lo.w_hi + hi.w_lo): its rounding error, which the residual stream carries unchanged
+ * through every layer, drops from 2^-9 to ~2^-17 relative for 0.4 % more tower FLOPs. */
+#define SETOK_VIT_PATCH_SPLIT 2
 
 size_t setok_vit_workspace_bytes(const setok_vit* vit, int B);
 /* images (device) [B,3,H,W] f32|bf16 -> features (device) [B, N(+1), C] f32|bf16.

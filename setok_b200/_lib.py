@@ -29,7 +29,12 @@ class VitLayer(C.Structure):
 class Vit(C.Structure):
     _fields_ = [("image_size", c_int), ("patch", c_int), ("hidden", c_int), ("heads", c_int), ("layers", c_int),
                 ("mlp", c_int), ("ln_eps", c_float), ("w_patch", c_void_p), ("cls", c_void_p), ("pos", c_void_p),
-                ("pre_ln_g", c_void_p), ("pre_ln_b", c_void_p), ("layer", C.POINTER(VitLayer))]
+                ("pre_ln_g", c_void_p), ("pre_ln_b", c_void_p), ("layer", C.POINTER(VitLayer)), ("flags", c_int)]
+
+
+VIT_RESIDUAL_F32 = 1
+VIT_PATCH_SPLIT = 2
+ABI_VERSION = 2
 
 
 class Attn(C.Structure):

@@ -11,16 +11,17 @@ using namespace setok;
 
 namespace {
 
-struct VitBufs { bf16* A; float* emb; bf16 *x, *h, *qkv, *ao, *u; };
+struct VitBufs { bf16* A; float* emb; void* x; bf16 *h, *qkv, *ao, *u; };   // x: bf16, or f32 with SETOK_VIT_RESIDUAL_F32
 
 int vit_carve(const setok_vit* v, int B, Arena& a, VitBufs* o) {
   const int P = (v->image_size / v->patch) * (v->image_size / v->patch);
   const int T = P + 1, C = v->hidden;
   const int Kp = static_cast<int>(round_up(3 * v->patch * v->patch, 64));
   const size_t R = static_cast<size_t>(B) * T;
-  o->A = a.take<bf16>(static_cast<size_t>(B) * P * Kp);
+  o->A = a.take<bf16>(static_cast<size_t>(B) * P * Kp * ((v->flags & SETOK_VIT_PATCH_SPLIT) ? 3 : 1));
   o->emb = a.take<float>(R * C);
-  o->x = a.take<bf16>(R * C);
+  if (v->flags & SETOK_VIT_RESIDUAL_F32) o->x = a.take<float>(R * C);
+  else o->x = a.take<bf16>(R * C);
   o->h = a.take<bf16>(R * C);
   o->qkv = a.take<bf16>(R * 3 * C);
   o->ao = a.take<bf16>(R * C);
@@ -39,18 +40,18 @@ int check_vit(const setok_vit* v) {
   return SETOK_OK;
 }
 
-// One pre-LN transformer layer on the bf16 residual stream x [R, C] of sequences of T rows:
+// One pre-LN transformer layer on the residual stream x [R, C] (bf16 or f32: xdt) of sequences of T rows:
 //   x += W_o MHSA(LN1(x)); x += W_2 act(W_1 LN2(x))      (CLIPEncoderLayer, modeling_clip.py:363-386; timm Block)
-int run_preln_layer(const setok_vit_layer& L, bf16* x, bf16* h, bf16* qkv, bf16* ao, bf16* u, int R, int T, int C, int F, int heads,
+int run_preln_layer(const setok_vit_layer& L, void* x, int xdt, bf16* h, bf16* qkv, bf16* ao, bf16* u, int R, int T, int C, int F, int heads,
                     float eps, int act, cudaStream_t stream) {
   const float scale = 1.0f / std::sqrt(static_cast<float>(C / heads));
-  SETOK_TRY(launch_layernorm(x, SETOK_BF16, h, SETOK_BF16, L.ln1_g, L.ln1_b, eps, R, C, nullptr, nullptr, stream));
+  SETOK_TRY(launch_layernorm(x, xdt, h, SETOK_BF16, L.ln1_g, L.ln1_b, eps, R, C, nullptr, nullptr, stream));
   SETOK_TRY(launch_gemm(GemmArgs{h, C, L.w_qkv, C, qkv, 3LL * C, SETOK_BF16, L.b_qkv, nullptr, 0, 0, SETOK_ACT_NONE, R, 3 * C, C, nullptr, 0}, stream));
   SETOK_TRY(launch_attention(qkv, ao, R, C, heads, scale, nullptr, nullptr, T, nullptr, stream));
-  SETOK_TRY(launch_gemm(GemmArgs{ao, C, L.w_o, C, x, C, SETOK_BF16, L.b_o, x, C, SETOK_BF16, SETOK_ACT_NONE, R, C, C, nullptr, 0}, stream));
-  SETOK_TRY(launch_layernorm(x, SETOK_BF16, h, SETOK_BF16, L.ln2_g, L.ln2_b, eps, R, C, nullptr, nullptr, stream));
+  SETOK_TRY(launch_gemm(GemmArgs{ao, C, L.w_o, C, x, C, xdt, L.b_o, x, C, xdt, SETOK_ACT_NONE, R, C, C, nullptr, 0}, stream));
+  SETOK_TRY(launch_layernorm(x, xdt, h, SETOK_BF16, L.ln2_g, L.ln2_b, eps, R, C, nullptr, nullptr, stream));
   SETOK_TRY(launch_gemm(GemmArgs{h, C, L.w_fc1, C, u, F, SETOK_BF16, L.b_fc1, nullptr, 0, 0, act, R, F, C, nullptr, 0}, stream));
-  SETOK_TRY(launch_gemm(GemmArgs{u, F, L.w_fc2, F, x, C, SETOK_BF16, L.b_fc2, x, C, SETOK_BF16, SETOK_ACT_NONE, R, C, F, nullptr, 0}, stream));
+  SETOK_TRY(launch_gemm(GemmArgs{u, F, L.w_fc2, F, x, C, xdt, L.b_fc2, x, C, xdt, SETOK_ACT_NONE, R, C, F, nullptr, 0}, stream));
   return SETOK_OK;
 }
 
@@ -144,6 +145,7 @@ int vit_forward_impl(const setok_vit* v, const void* images, int image_dtype, in
   const int G = v->image_size / v->patch, P = G * G, T = P + 1, C = v->hidden, F = v->mlp;
   const int Kp = static_cast<int>(round_up(3 * v->patch * v->patch, 64));
   const int R = B * T;
+  const int split = (v->flags & SETOK_VIT_PATCH_SPLIT) ? 1 : 0;
   Arena a(workspace, workspace_bytes);
   VitBufs w;
   vit_carve(v, B, a, &w);
@@ -152,22 +154,24 @@ int vit_forward_impl(const setok_vit* v, const void* images, int image_dtype, in
   // rows past each image's CLS slot and adds the position embedding; CLS rows; pre_layrnorm.
   if (image_dtype == SETOK_U8) {
     SETOK_REQUIRE(u8norm != nullptr, SETOK_ERR_BAD_ARG, "vit_forward: uint8 images need the normalisation constants (setok_vit_forward_u8)");
-    SETOK_TRY(launch_im2col_u8(static_cast<const uint8_t*>(images), u8norm, w.A, B, v->image_size, v->image_size, v->patch, Kp, stream));
+    SETOK_TRY(launch_im2col_u8(static_cast<const uint8_t*>(images), u8norm, w.A, B, v->image_size, v->image_size, v->patch, Kp, split, stream));
   } else {
-    SETOK_TRY(launch_im2col(images, image_dtype, w.A, B, v->image_size, v->image_size, v->patch, Kp, stream));
+    SETOK_TRY(launch_im2col(images, image_dtype, w.A, B, v->image_size, v->image_size, v->patch, Kp, split, stream));
   }
-  SETOK_TRY(launch_gemm(GemmArgs{w.A, Kp, v->w_patch, Kp, w.emb, C, SETOK_F32, nullptr, v->pos, C, SETOK_F32, SETOK_ACT_NONE, B * P, C, Kp, nullptr, P}, stream));
+  const int Ke = split ? 3 * Kp : Kp;     // split: rows [hi | lo | hi] against weight rows [w_hi | w_hi | w_lo]
+  SETOK_TRY(launch_gemm(GemmArgs{w.A, Ke, v->w_patch, Ke, w.emb, C, SETOK_F32, nullptr, v->pos, C, SETOK_F32, SETOK_ACT_NONE, B * P, C, Ke, nullptr, P}, stream));
   SETOK_TRY(launch_cls_rows(w.emb, v->cls, v->pos, B, T, C, stream));
-  SETOK_TRY(launch_layernorm(w.emb, SETOK_F32, w.x, SETOK_BF16, v->pre_ln_g, v->pre_ln_b, v->ln_eps, R, C, nullptr, nullptr, stream));
+  const int xdt = (v->flags & SETOK_VIT_RESIDUAL_F32) ? SETOK_F32 : SETOK_BF16;
+  SETOK_TRY(launch_layernorm(w.emb, SETOK_F32, w.x, xdt, v->pre_ln_g, v->pre_ln_b, v->ln_eps, R, C, nullptr, nullptr, stream));
 
   for (int l = 0; l < n_layers_run; ++l) {
     const setok_vit_layer& L = v->layer[l];
     SETOK_REQUIRE(L.w_qkv && L.b_qkv && L.w_o && L.b_o && L.w_fc1 && L.b_fc1 && L.w_fc2 && L.b_fc2 && L.ln1_g && L.ln1_b && L.ln2_g && L.ln2_b,
                   SETOK_ERR_BAD_ARG, "vit_forward: null weights in layer %d", l);
-    SETOK_TRY(run_preln_layer(L, w.x, w.h, w.qkv, w.ao, w.u, R, T, C, F, v->heads, v->ln_eps, SETOK_ACT_QUICK_GELU, stream));
+    SETOK_TRY(run_preln_layer(L, w.x, xdt, w.h, w.qkv, w.ao, w.u, R, T, C, F, v->heads, v->ln_eps, SETOK_ACT_QUICK_GELU, stream));
   }
   // feature_select (clip_encoder.py:40-48)
-  SETOK_TRY(launch_select_rows(w.x, features, feature_dtype, B, T, keep_cls ? 0 : 1, C, pos_add, stream));
+  SETOK_TRY(launch_select_rows(w.x, xdt, features, feature_dtype, B, T, keep_cls ? 0 : 1, C, pos_add, stream));
   return SETOK_OK;
 }
 }  // namespace
@@ -399,7 +403,7 @@ extern "C" int setok_detok_forward(const setok_detok* d, const void* tokens, int
     const setok_vit_layer& L = d->block[l];
     SETOK_REQUIRE(L.w_qkv && L.b_qkv && L.w_o && L.b_o && L.w_fc1 && L.b_fc1 && L.w_fc2 && L.b_fc2 && L.ln1_g && L.ln1_b && L.ln2_g && L.ln2_b,
                   SETOK_ERR_BAD_ARG, "detok_forward: null weights in decoder block %d", l);
-    SETOK_TRY(run_preln_layer(L, w.x, w.hx, w.qkv, w.ctx, w.u, R, Q, Dd, Fd, d->dec_heads, d->dec_ln_eps, SETOK_ACT_GELU_ERF, stream));
+    SETOK_TRY(run_preln_layer(L, w.x, SETOK_BF16, w.hx, w.qkv, w.ctx, w.u, R, Q, Dd, Fd, d->dec_heads, d->dec_ln_eps, SETOK_ACT_GELU_ERF, stream));
   }
   SETOK_TRY(launch_layernorm(w.x, SETOK_BF16, out, out_dtype, d->norm_g, d->norm_b, d->dec_ln_eps, R, Dd, nullptr, nullptr, stream));
   return SETOK_OK;

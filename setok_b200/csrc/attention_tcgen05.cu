@@ -292,10 +292,7 @@ int launch_attention_tcgen05(const void* qkv, void* out, int B, int T, int C, in
   r = enc(&tm_kv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(qkv), gdim, gstr, box_kv, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(SETOK_ERR_CUDA, "attention: cuTensorMapEncodeTiled (kv) failed with CUresult %d", (int)r);
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(attn_tcgen05_hd64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM); });
-  SETOK_CUDA_OK(attr_err);
+  SETOK_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(attn_tcgen05_hd64_kernel), ATT_SMEM));
   dim3 grid(ceil_div(T, QT), heads, B);
   SETOK_CUDA_OK(launch_pdl(attn_tcgen05_hd64_kernel, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tm, tm_kv, static_cast<bf16*>(out), T, heads, C,
                            scale * 1.4426950408889634f, g_attn_trace));

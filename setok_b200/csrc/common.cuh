@@ -63,7 +63,9 @@ inline int fail(int code, const char* fmt, ...) {
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
-int num_sms();
+int num_sms();                                            // of the current device (cached per device)
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (current device, kernel)
+int ensure_dynamic_smem(const void* kernel, int bytes);
 
 // Bump allocator over the caller's workspace (256-byte aligned slices).
 struct Arena {
@@ -368,21 +370,6 @@ __device__ __forceinline__ void umma_commit_2cta_mc(uint32_t bar, uint16_t cta_m
                ::"r"(bar), "h"(cta_mask) : "memory");
 }
 
-// ---- legacy warp MMA (used by the small-head_dim attention kernel) --------------------------------
-__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
 #endif  // __CUDACC__
 
 // ---------------------------------------------------------------------------------------------

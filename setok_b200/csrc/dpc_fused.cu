@@ -29,8 +29,6 @@
 #include "common.cuh"
 
 #include <cmath>
-#include <mutex>
-#include <set>
 
 namespace setok {
 int g_dpc_fused = 1;   // 0: multi-kernel path only; 1: fused, 4-term split; 2: fused, 3-term split (lo.lo dropped)
@@ -598,15 +596,7 @@ int launch_dpc_fused(const void* feats, int feat_dtype, const float* pos, const 
 #define SETOK_FZ_PICK(KS) (fb ? dpc_fused_kernel<KS, true> : dpc_fused_kernel<KS, false>)
   KernelFn fn = k <= 16 ? SETOK_FZ_PICK(16) : (k <= 32 ? SETOK_FZ_PICK(32) : SETOK_FZ_PICK(64));
 #undef SETOK_FZ_PICK
-  static std::mutex attr_mu;
-  static std::set<KernelFn> attr_done;
-  {
-    std::lock_guard<std::mutex> lk(attr_mu);
-    if (!attr_done.count(fn)) {
-      SETOK_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, FZ_SMEM_BYTES));
-      attr_done.insert(fn);
-    }
-  }
+  SETOK_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(fn), FZ_SMEM_BYTES));
   const int grid = B < num_sms() ? B : num_sms();
   fn<<<grid, FZ_THREADS, FZ_SMEM_BYTES, stream>>>(tm, p);
   SETOK_LAUNCH_CHECK();

@@ -16,9 +16,6 @@
 // (m_dev) so data-dependent row counts need no host sync.
 #include "common.cuh"
 
-#include <mutex>
-#include <set>
-
 namespace setok {
 namespace {
 
@@ -202,22 +199,30 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const long long dbase = static_cast<long long>(bt) * p.d_batch_stride;
       bool waited = false;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + half * 128);
-      // bf16 residual (the ViT's out_proj / fc2): the whole tile's residual is requested before waiting for the
-      // accumulator, so the HBM latency overlaps the MMAs instead of being paid once per 32-column chunk
-      constexpr bool kTilePrefetch = (RES == 1);
-      uint2 rt[4][8];
-      if (kTilePrefetch) {
+      // Residual of the ViT's out_proj / fc2 (x += ...): requested ahead of its use so that the HBM latency overlaps the
+      // MMAs instead of being paid once per 32-column chunk.  bf16: the whole tile (4 chunks, 64 registers) before waiting
+      // for the accumulator; f32: a ring of two chunks (64 registers), chunk c + 2 requested when chunk c has been consumed.
+      constexpr int PF = (REMAP == 0 && RES == 1) ? 4 : ((REMAP == 0 && RES == 2) ? 2 : 0);
+      uint2 rt[PF > 0 && RES == 1 ? PF : 1][8];
+      float4 rtf[PF > 0 && RES == 2 ? PF : 1][8];
+      auto prefetch = [&](int ch, int slot) {
+        const int col = n0 + ch * 32 + 4 * j;
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          const int col = n0 + ch * 32 + 4 * j;
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int grow = row0 + it * 4 + rsub;
-            rt[ch][it] = make_uint2(0u, 0u);
-            if (grow < M_eff && col < p.N)
-              rt[ch][it] = *reinterpret_cast<const uint2*>(static_cast<const bf16*>(p.res) + static_cast<long long>(bt) * p.r_batch_stride + static_cast<long long>(grow) * p.ldr + col);
+        for (int it = 0; it < 8; ++it) {
+          const int grow = row0 + it * 4 + rsub;
+          const bool ok = grow < M_eff && col < p.N;
+          if (RES == 1) {
+            rt[slot][it] = make_uint2(0u, 0u);
+            if (ok) rt[slot][it] = *reinterpret_cast<const uint2*>(static_cast<const bf16*>(p.res) + static_cast<long long>(bt) * p.r_batch_stride + static_cast<long long>(grow) * p.ldr + col);
+          } else {
+            rtf[slot][it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok) rtf[slot][it] = *reinterpret_cast<const float4*>(static_cast<const float*>(p.res) + static_cast<long long>(bt) * p.r_batch_stride + static_cast<long long>(grow) * p.ldr + col);
           }
         }
+      };
+      if (PF > 0) {
+#pragma unroll
+        for (int ch = 0; ch < PF; ++ch) prefetch(ch, ch);
       }
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
@@ -228,9 +233,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         // residual prefetch in the coalesced layout: in flight while the accumulator is drained and transposed
         uint2 rb[8];
         float4 rf[8];
-        if (kTilePrefetch) {
+        if (PF > 0) {
 #pragma unroll
-          for (int it = 0; it < 8; ++it) rb[it] = rt[ch][it];
+          for (int it = 0; it < 8; ++it) { if (RES == 1) rb[it] = rt[ch % PF][it]; else rf[it] = rtf[ch % PF][it]; }
+          if (PF < 4 && ch + PF < 4) prefetch(ch + PF, ch % PF);
         } else if (res_kind == 1) {
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
@@ -398,15 +404,7 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   }
 #undef SETOK_PICK
   const int smem_bytes = cg == 2 ? Cfg<2>::SMEM_BYTES : Cfg<1>::SMEM_BYTES;
-  static std::mutex attr_mu;
-  static std::set<KernelFn> attr_done;
-  {
-    std::lock_guard<std::mutex> lk(attr_mu);
-    if (!attr_done.count(fn)) {
-      SETOK_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-      attr_done.insert(fn);
-    }
-  }
+  SETOK_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(fn), smem_bytes));
   CUtensorMap tmA, tmB;
   SETOK_TRY(make_tmap_bf16(&tmA, g.A, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)g.lda, (uint64_t)g.batch, (uint64_t)g.a_batch_stride, BK, BM));
   if (g.w_mn_major)   // W is [K, N]: box = 64 N-columns (128 B) x 64 K-rows, one per 64-column atom of the B tile

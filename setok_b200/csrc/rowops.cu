@@ -107,9 +107,23 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const TI* __restrict__ i
 }
 
 // ---- patch embedding im2col: images [B,3,H,W] -> A [B*P, Kp] bf16, columns (c, ky, kx), zero pad ----
+// split: the row is [hi | lo | hi] (3 * Kp columns) with x = hi + lo (bf16 + bf16): against the weight row
+// [w_hi | w_hi | w_lo] one GEMM with K = 3 Kp evaluates x.w = hi.w_hi + lo.w_hi + hi.w_lo, i.e. the patch embedding to
+// ~2^-17 instead of the 2^-9 of bf16-rounded pixels and weights (the embedding's rounding error is carried unchanged down
+// the residual stream, so it would otherwise set the floor of the whole tower's error)
+__device__ __forceinline__ void store_patch_pair(bf16* __restrict__ A, long long row, int Kp, int cp, float v0, float v1, int split) {
+  const uint32_t hi = pack_bf16x2(v0, v1);
+  if (!split) { *reinterpret_cast<uint32_t*>(A + row * Kp + cp * 2) = hi; return; }
+  const float2 hf = unpack_bf16x2(hi);
+  const uint32_t lo = pack_bf16x2(v0 - hf.x, v1 - hf.y);
+  bf16* r = A + row * (3LL * Kp) + cp * 2;
+  *reinterpret_cast<uint32_t*>(r) = hi;
+  *reinterpret_cast<uint32_t*>(r + Kp) = lo;
+  *reinterpret_cast<uint32_t*>(r + 2 * Kp) = hi;
+}
 template <class TI>
 __global__ void __launch_bounds__(256) im2col_kernel(const TI* __restrict__ img, bf16* __restrict__ A, int B, int H, int W,
-                                                     int patch, int Kp) {
+                                                     int patch, int Kp, int split) {
   const int gw = W / patch, gh = H / patch;
   const int K = 3 * patch * patch;
   const long long total = static_cast<long long>(B) * gh * gw * (Kp / 2);
@@ -133,14 +147,14 @@ __global__ void __launch_bounds__(256) im2col_kernel(const TI* __restrict__ img,
         v[e] = 0.f;
       }
     }
-    *reinterpret_cast<uint32_t*>(A + row * Kp + cp * 2) = pack_bf16x2(v[0], v[1]);
+    store_patch_pair(A, row, Kp, cp, v[0], v[1], split);
   }
 }
 
 // uint8 pixels: CLIPImageProcessor's rescale + normalize (transformers 4.46.3, numpy float32 arithmetic) fused into the im2col
 //   x = lut[u8] (= float32(float64(u8) * rescale_factor), built on the host);  y = (x - mean[c]) / std[c], rounded separately
 __global__ void __launch_bounds__(256) im2col_u8_kernel(const uint8_t* __restrict__ img, bf16* __restrict__ A, int B, int H, int W, int patch,
-                                                        int Kp, const setok_u8_norm nrm) {
+                                                        int Kp, int split, const setok_u8_norm nrm) {
   __shared__ float lut[256];
   lut[threadIdx.x] = nrm.lut[threadIdx.x];
   __syncthreads();
@@ -167,7 +181,7 @@ __global__ void __launch_bounds__(256) im2col_u8_kernel(const uint8_t* __restric
         v[e] = __fdiv_rn(__fsub_rn(lut[u], nrm.mean[c]), nrm.std[c]);
       }
     }
-    *reinterpret_cast<uint32_t*>(A + row * Kp + cp * 2) = pack_bf16x2(v[0], v[1]);
+    store_patch_pair(A, row, Kp, cp, v[0], v[1], split);
   }
 }
 
@@ -183,8 +197,8 @@ __global__ void cls_rows_kernel(float* __restrict__ emb, const float* __restrict
 
 // features[b, t', :] = x[b*T + skip + t', :] (+ pos[t', :])  (dtype conversion bf16 -> out).  With `pos` the output is
 // the position-embedded tensor of tokenizer.py:168 (feature_select and the add fused in one pass).
-template <class TO>
-__global__ void __launch_bounds__(256) select_rows_kernel(const bf16* __restrict__ x, TO* __restrict__ out, int B, int T, int skip, int C,
+template <class TI, class TO>
+__global__ void __launch_bounds__(256) select_rows_kernel(const TI* __restrict__ x, TO* __restrict__ out, int B, int T, int skip, int C,
                                                           const float* __restrict__ pos) {
   const int To = T - skip;
   const int nvec = C >> 2;
@@ -195,7 +209,7 @@ __global__ void __launch_bounds__(256) select_rows_kernel(const bf16* __restrict
     const long long r = i / nvec;
     const int t = static_cast<int>(r % To);
     const long long b = r / To;
-    float4 v = Vec4<bf16>::load(x + ((b * T + skip + t) * C + vi * 4));
+    float4 v = Vec4<TI>::load(x + ((b * T + skip + t) * C + vi * 4));
     if (pos != nullptr) {
       const float4 q = __ldg(reinterpret_cast<const float4*>(pos + static_cast<long long>(t) * C + vi * 4));
       v.x = __fadd_rn(v.x, q.x); v.y = __fadd_rn(v.y, q.y); v.z = __fadd_rn(v.z, q.z); v.w = __fadd_rn(v.w, q.w);
@@ -368,19 +382,19 @@ int launch_masked_softmax(const float* S, void* P, const int32_t* seg_off, const
   return SETOK_OK;
 }
 
-int launch_im2col(const void* images, int image_dtype, void* A, int B, int H, int W, int patch, int Kp, cudaStream_t stream) {
+int launch_im2col(const void* images, int image_dtype, void* A, int B, int H, int W, int patch, int Kp, int split, cudaStream_t stream) {
   const long long total = static_cast<long long>(B) * (H / patch) * (W / patch) * (Kp / 2);
   const int grid = grid_for(total, 256, 16);
-  if (image_dtype == SETOK_F32) im2col_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(images), static_cast<bf16*>(A), B, H, W, patch, Kp);
-  else if (image_dtype == SETOK_BF16) im2col_kernel<bf16><<<grid, 256, 0, stream>>>(static_cast<const bf16*>(images), static_cast<bf16*>(A), B, H, W, patch, Kp);
+  if (image_dtype == SETOK_F32) im2col_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(images), static_cast<bf16*>(A), B, H, W, patch, Kp, split);
+  else if (image_dtype == SETOK_BF16) im2col_kernel<bf16><<<grid, 256, 0, stream>>>(static_cast<const bf16*>(images), static_cast<bf16*>(A), B, H, W, patch, Kp, split);
   else return fail(SETOK_ERR_BAD_ARG, "im2col: bad image dtype %d", image_dtype);
   SETOK_LAUNCH_CHECK();
   return SETOK_OK;
 }
 
-int launch_im2col_u8(const uint8_t* images, const setok_u8_norm* norm, void* A, int B, int H, int W, int patch, int Kp, cudaStream_t stream) {
+int launch_im2col_u8(const uint8_t* images, const setok_u8_norm* norm, void* A, int B, int H, int W, int patch, int Kp, int split, cudaStream_t stream) {
   const long long total = static_cast<long long>(B) * (H / patch) * (W / patch) * (Kp / 2);
-  im2col_u8_kernel<<<grid_for(total, 256, 16), 256, 0, stream>>>(images, static_cast<bf16*>(A), B, H, W, patch, Kp, *norm);
+  im2col_u8_kernel<<<grid_for(total, 256, 16), 256, 0, stream>>>(images, static_cast<bf16*>(A), B, H, W, patch, Kp, split, *norm);
   SETOK_LAUNCH_CHECK();
   return SETOK_OK;
 }
@@ -425,12 +439,15 @@ int launch_add_pos_rows(const float* in, const float* pos, void* out_bf16, int r
   return SETOK_OK;
 }
 
-int launch_select_rows(const void* x_bf16, void* out, int out_dtype, int B, int T, int skip, int C, const float* pos, cudaStream_t stream) {
+int launch_select_rows(const void* x, int x_dtype, void* out, int out_dtype, int B, int T, int skip, int C, const float* pos, cudaStream_t stream) {
   const long long total = static_cast<long long>(B) * (T - skip) * (C / 4);
   const int grid = grid_for(total, 256, 16);
-  if (out_dtype == SETOK_F32) select_rows_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const bf16*>(x_bf16), static_cast<float*>(out), B, T, skip, C, pos);
-  else if (out_dtype == SETOK_BF16) select_rows_kernel<bf16><<<grid, 256, 0, stream>>>(static_cast<const bf16*>(x_bf16), static_cast<bf16*>(out), B, T, skip, C, pos);
-  else return fail(SETOK_ERR_BAD_ARG, "select_rows: bad dtype %d", out_dtype);
+  SETOK_REQUIRE((x_dtype == SETOK_F32 || x_dtype == SETOK_BF16) && (out_dtype == SETOK_F32 || out_dtype == SETOK_BF16), SETOK_ERR_BAD_ARG,
+                "select_rows: bad dtype %d -> %d", x_dtype, out_dtype);
+#define SETOK_SEL(TI, TO) select_rows_kernel<TI, TO><<<grid, 256, 0, stream>>>(static_cast<const TI*>(x), static_cast<TO*>(out), B, T, skip, C, pos)
+  if (x_dtype == SETOK_BF16) { if (out_dtype == SETOK_F32) SETOK_SEL(bf16, float); else SETOK_SEL(bf16, bf16); }
+  else { if (out_dtype == SETOK_F32) SETOK_SEL(float, float); else SETOK_SEL(float, bf16); }
+#undef SETOK_SEL
   SETOK_LAUNCH_CHECK();
   return SETOK_OK;
 }

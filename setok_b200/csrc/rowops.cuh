@@ -3,10 +3,10 @@
 #include "common.cuh"
 
 namespace setok {
-int launch_im2col(const void* images, int image_dtype, void* A, int B, int H, int W, int patch, int Kp, cudaStream_t stream);
-int launch_im2col_u8(const uint8_t* images, const setok_u8_norm* norm, void* A, int B, int H, int W, int patch, int Kp, cudaStream_t stream);
+int launch_im2col(const void* images, int image_dtype, void* A, int B, int H, int W, int patch, int Kp, int split, cudaStream_t stream);
+int launch_im2col_u8(const uint8_t* images, const setok_u8_norm* norm, void* A, int B, int H, int W, int patch, int Kp, int split, cudaStream_t stream);
 int launch_cls_rows(float* emb, const float* cls, const float* pos, int B, int T, int C, cudaStream_t stream);
-int launch_select_rows(const void* x_bf16, void* out, int out_dtype, int B, int T, int skip, int C, const float* pos, cudaStream_t stream);
+int launch_select_rows(const void* x, int x_dtype, void* out, int out_dtype, int B, int T, int skip, int C, const float* pos, cudaStream_t stream);
 int launch_sort_by_cluster(const int64_t* idx_cluster, const int32_t* num_clusters, const int32_t* offsets, int B, int N,
                            int32_t* perm, int32_t* row_seg, int32_t* seg_off, cudaStream_t stream);
 int launch_gather_rows(const float* in, float* out, const int32_t* perm, int rows, int C, cudaStream_t stream);

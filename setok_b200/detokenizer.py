@@ -26,6 +26,7 @@ import torch.nn as nn
 
 from . import _lib, ops
 from ._lib import SetokError
+from ._pack import PackedParams
 from .ragged import RaggedTokens
 from .tokenizer import Attention, Mlp, PositionalEncoding2D, _bf16, _f32
 
@@ -107,7 +108,7 @@ class _Mapper(nn.Module):
         self.encoder = _BertEncoder(hidden, inter, eps, layers, freq)
 
 
-class SetokDeTokenizer(nn.Module):
+class SetokDeTokenizer(PackedParams, nn.Module):
     def __init__(self, token_feat_dim: Optional[int] = 4096, hidden_dim: Optional[int] = 4096, patch_size: Optional[int] = 14,
                  image_size: Optional[int] = 256, decoder_embed_dim: Optional[int] = 4096, decoder_nheads: Optional[int] = 16,
                  proj_drop: Optional[float] = 0.2, attn_drop: Optional[float] = 0.2, decoder_depth: Optional[int] = 16,
@@ -169,17 +170,6 @@ class SetokDeTokenizer(nn.Module):
         pass
 
     # -- packing -------------------------------------------------------------------------------
-    def _apply(self, fn, *a, **k):
-        self._packed = None
-        return super()._apply(fn, *a, **k)
-
-    def load_state_dict(self, *a, **k):
-        self._packed = None
-        return super().load_state_dict(*a, **k)
-
-    def invalidate(self):
-        self._packed = None
-
     @property
     def device(self):
         return self.mask_tokens.device
@@ -254,7 +244,7 @@ class SetokDeTokenizer(nn.Module):
     def forward(self, x, attention_masks: Optional[torch.Tensor] = None, out_dtype=None) -> torch.Tensor:
         """``x``: the reference's padded tokens (B, K_max, C_tok) with ``attention_masks`` (B, K_max) in {0, 1}, or a
         ``RaggedTokens`` (packed rows + offsets, nothing padded).  Returns (B, (image_size/patch)^2, decoder_embed_dim)."""
-        d = (self._packed or self._pack())[0]
+        d = self._packed_get()[0]
         dev = self.device
         if isinstance(x, RaggedTokens):
             tokens, offsets = x.data, x.offsets

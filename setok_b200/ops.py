@@ -46,11 +46,14 @@ _ws_cache = {}
 
 
 def workspace(dev: torch.device, nbytes: int, tag: str) -> torch.Tensor:
-    """Grow-only per-(device, tag) scratch buffer, so steady-state steps allocate nothing."""
-    key = (dev.index, tag)
+    """Grow-only scratch buffer per (device, CUDA stream, tag), so steady-state steps allocate nothing and two streams
+    (or threads, each on its own stream) running the same op never share scratch."""
+    stream = torch.cuda.current_stream(dev)
+    key = (dev.index, stream.cuda_stream, tag)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
+        buf.record_stream(stream)
         _ws_cache[key] = buf
     return buf
 

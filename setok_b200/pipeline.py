@@ -1,12 +1,21 @@
 """Host <-> device streaming around the tokenizer (the end-to-end path a data loader drives).
 
-`stream_tokenize` software-pipelines three things that would otherwise serialise each step:
-the H2D copy of the *next* batch (pinned host memory, on a copy stream), the kernel launches of the
-current batch, and the D2H read-back of the *previous* batch's ragged result on its own stream (its row count is
-data-dependent, so reading it needs a host sync — which waits only for that batch, while the GPU runs the next one).
+`stream_tokenize` software-pipelines everything that would otherwise serialise a step:
+
+* the H2D copy of the *next* batch (pinned host memory, on a copy stream) is issued before anything else happens to the
+  current batch;
+* the kernel launches of the current batch run on the caller's stream;
+* with ``gather`` (a ``dist.RaggedAllGather``) the data-parallel exchange of batch i is split around the launch of batch
+  i+1: its small header all-gather is enqueued right after batch i's kernels, the host reads that header -- and sizes /
+  enqueues the row all-gather on the communication stream -- only after batch i+1 has been launched, so neither the host
+  read nor the NCCL transfer ever idles the compute stream;
+* the D2H read-back of a finished batch's ragged result runs on its own stream (its row count is data-dependent, so
+  reading it needs a host sync -- which waits only for that batch, while the GPU runs the next ones).
+
 Every batch is still copied in and its result copied out; nothing is cached across steps."""
 from __future__ import annotations
 
+from collections import deque
 from typing import Callable, Iterable, Iterator, Optional, Tuple
 
 import torch
@@ -27,15 +36,14 @@ class HostResult:
 
 class _Readback:
     """D2H of one batch's ragged result on a dedicated stream.  The row count is data-dependent, so the read-back is two
-    hops (offsets, then the packed rows); both wait only for THIS batch's kernels (an event), never for the batch the
-    main stream is already running, and land in pinned host memory."""
+    hops (offsets, then the packed rows) unless the host already knows the offsets (a gathered batch); both wait only for
+    THIS batch's kernels (an event), never for the batch the main stream is already running, and land in pinned memory."""
 
-    def __init__(self, out, d2h: torch.cuda.Stream, main: torch.cuda.Stream):
+    def __init__(self, out, d2h: torch.cuda.Stream, after: torch.cuda.Event):
         self.rt, self.idx, self.score = out
         self.d2h = d2h
-        done = torch.cuda.Event()
-        done.record(main)
-        d2h.wait_event(done)
+        d2h.wait_event(after)
+        known = self.rt._host is not None            # offsets already on the host (RaggedAllGather.finish)
         with torch.cuda.stream(d2h):
             for t in (self.rt.data, self.rt.offsets, self.idx, self.score):
                 t.record_stream(d2h)
@@ -45,24 +53,31 @@ class _Readback:
             self.h_idx.copy_(self.idx, non_blocking=True)
             self.h_score = torch.empty(self.score.shape, dtype=self.score.dtype, pin_memory=True)
             self.h_score.copy_(self.score, non_blocking=True)
+            self.h_tok = None
+            if known:
+                self.h_tok = self._rows(self.rt.total)
             self.ev = torch.cuda.Event()
             self.ev.record(d2h)
 
+    def _rows(self, total: int):
+        h_tok = torch.empty((total, self.rt.data.shape[1]), dtype=self.rt.data.dtype, pin_memory=True)
+        h_tok.copy_(self.rt.data[:total], non_blocking=True)
+        return h_tok
+
     def result(self) -> HostResult:
         self.ev.synchronize()
-        total = int(self.h_off[-1])
-        with torch.cuda.stream(self.d2h):
-            h_tok = torch.empty((total, self.rt.data.shape[1]), dtype=self.rt.data.dtype, pin_memory=True)
-            h_tok.copy_(self.rt.data[:total], non_blocking=True)
-        self.d2h.synchronize()
-        return HostResult(h_tok, self.h_off, self.h_idx, self.h_score)
+        if self.h_tok is None:
+            with torch.cuda.stream(self.d2h):
+                self.h_tok = self._rows(int(self.h_off[-1]))
+            self.d2h.synchronize()
+        return HostResult(self.h_tok, self.h_off, self.h_idx, self.h_score)
 
 
 def stream_tokenize(tokenizer, host_batches: Iterable[Tuple[torch.Tensor, Optional[torch.Tensor]]],
-                    post: Optional[Callable] = None, **forward_kwargs) -> Iterator[HostResult]:
-    """host_batches yields (pinned images (B,3,H,W), pinned noise (B,N) or None).  Yields one HostResult per batch,
-    in order.  `post(ragged, idx, score) -> (ragged, idx, score)` runs on the device after the tokenizer (e.g. the
-    projector or the data-parallel all-gather)."""
+                    post: Optional[Callable] = None, gather=None, **forward_kwargs) -> Iterator[HostResult]:
+    """host_batches yields (pinned images (B,3,H,W) float or uint8, pinned noise (B,N) or None).  Yields one HostResult per
+    batch, in order.  `post(ragged, idx, score) -> (ragged, idx, score)` runs on the device right after the tokenizer (e.g.
+    the projector); `gather` (dist.RaggedAllGather) then repacks the ranks' ragged outputs into the global batch."""
     dev = tokenizer.device
     copy_stream = torch.cuda.Stream(dev)
     d2h_stream = torch.cuda.Stream(dev)
@@ -77,28 +92,47 @@ def stream_tokenize(tokenizer, host_batches: Iterable[Tuple[torch.Tensor, Option
             ev.record(copy_stream)
         return d_img, d_noise, ev
 
+    def read(out, after):
+        return _Readback(out, d2h_stream, after)
+
     it = iter(host_batches)
     try:
         nxt = upload(next(it))
     except StopIteration:
         return
-    prev = None
+    pending_gather = None                # (handle, idx, score) of the batch whose row exchange is still to be enqueued
+    reads = deque()                      # read-backs in flight, oldest first
     while nxt is not None:
         d_img, d_noise, ev = nxt
         main.wait_event(ev)
         d_img.record_stream(main)
         if d_noise is not None:
             d_noise.record_stream(main)
+        try:
+            nxt = upload(next(it))          # next batch's H2D is in flight before this batch's kernels are even launched
+        except StopIteration:
+            nxt = None
         out = tokenizer(d_img, noise=d_noise, **forward_kwargs)
         if post is not None:
             out = post(*out)
-        try:
-            nxt = upload(next(it))          # next batch's H2D overlaps this batch's kernels
-        except StopIteration:
-            nxt = None
-        cur = _Readback(out, d2h_stream, main)
-        if prev is not None:
-            yield prev.result()             # previous batch's D2H (and its host sync) overlaps this batch's kernels
-        prev = cur
-    if prev is not None:
-        yield prev.result()
+        if gather is not None:
+            handle = gather.start(out[0])   # header exchange enqueued behind this batch's kernels; no host wait
+            if pending_gather is not None:
+                reads.append(_finish_gather(gather, pending_gather, read))
+            pending_gather = (handle, out[1], out[2])
+        else:
+            done = torch.cuda.Event()
+            done.record(main)
+            reads.append(read(out, done))
+        while len(reads) > 1:
+            yield reads.popleft().result()   # an older batch's D2H (and its host sync) overlaps the newer batches' kernels
+    if pending_gather is not None:
+        reads.append(_finish_gather(gather, pending_gather, read))
+    while reads:
+        yield reads.popleft().result()
+
+
+def _finish_gather(gather, pending, read):
+    handle, idx, score = pending
+    rt = gather.finish(handle, wait=False)   # host reads that batch's header (long since landed), row exchange on the comm stream
+    return read((rt, idx, score), rt.ready)

@@ -16,6 +16,7 @@ import torch.nn as nn
 
 from . import _lib, ops
 from ._lib import SetokError
+from ._pack import PackedParams
 from .ragged import RaggedTokens
 
 
@@ -28,7 +29,7 @@ class IdentityMap(nn.Module):
         return {"mm_projector_type": "identity"}
 
 
-class _PackedProjector:
+class _PackedProjector(PackedParams):
     """Mixin: packs the Linear chain and calls setok_project."""
 
     def _linears(self):
@@ -36,17 +37,6 @@ class _PackedProjector:
 
     def _norm(self) -> Optional[nn.LayerNorm]:
         return None
-
-    def _apply(self, fn, *a, **k):
-        self._packed = None
-        return super()._apply(fn, *a, **k)
-
-    def load_state_dict(self, *a, **k):
-        self._packed = None
-        return super().load_state_dict(*a, **k)
-
-    def invalidate(self):
-        self._packed = None
 
     def _pack(self):
         lins = self._linears()
@@ -69,7 +59,7 @@ class _PackedProjector:
 
     @torch.no_grad()
     def forward(self, x, out_dtype=None):
-        proj, keep = getattr(self, "_packed", None) or self._pack()
+        proj, keep = self._packed_get()
         ragged = isinstance(x, RaggedTokens)
         data = x.data if ragged else x
         lead = None
@@ -98,7 +88,6 @@ class _PackedProjector:
 class LinearProjector(_PackedProjector, nn.Linear):
     def __init__(self, in_features, out_features):
         nn.Linear.__init__(self, in_features, out_features)
-        self._packed = None
 
     def _linears(self):
         return [self]
@@ -107,7 +96,6 @@ class LinearProjector(_PackedProjector, nn.Linear):
 class MlpProjector(_PackedProjector, nn.Sequential):
     def __init__(self, *modules):
         nn.Sequential.__init__(self, *modules)
-        self._packed = None
 
     def _linears(self):
         return [m for m in self if isinstance(m, nn.Linear)]

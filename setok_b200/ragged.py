@@ -81,7 +81,14 @@ class RaggedTokens:
         return self.data.device
 
     def to(self, *a, **k) -> "RaggedTokens":
-        r = RaggedTokens(self.data.to(*a, **k), self.offsets, self.index_down)
+        """Like Tensor.to for the packed rows; a device move takes ``offsets`` / ``index_down`` along (their integer dtypes
+        are kept)."""
+        data = self.data.to(*a, **k)
+        offsets, down = self.offsets, self.index_down
+        if data.device != self.data.device:
+            offsets = offsets.to(data.device)
+            down = None if down is None else down.to(data.device)
+        r = RaggedTokens(data, offsets, down)
         r._host = self._host
         return r
 

@@ -39,9 +39,6 @@ def prepare_inputs_labels_for_multimodal(input_ids: torch.Tensor, position_ids: 
     if dtype not in (torch.float32, torch.bfloat16):
         raise SetokError(f"unsupported embedding dtype {dtype} (float32 or bfloat16 expected)")
     weight = weight.detach().contiguous()
-    rows = rows.to(device=dev, dtype=dtype).contiguous()
-    if rows.shape[0] == 0:
-        rows = weight.new_zeros(1, weight.shape[1])
     offsets = offsets.to(device=dev, dtype=torch.int32).contiguous()
     ids = input_ids.to(device=dev, dtype=torch.int64).contiguous()
     B, L = ids.shape
@@ -52,14 +49,23 @@ def prepare_inputs_labels_for_multimodal(input_ids: torch.Tensor, position_ids: 
     max_len = torch.empty(1, dtype=torch.int32, device=dev)
     lib = _lib.load()
     limit = int(tokenizer_model_max_length) if tokenizer_model_max_length is not None else 2 ** 30
-    # one workspace for both phases (the plan lives in its first slices): sized for the column upper bound L + all image rows,
-    # which costs 4 bytes per column
-    ws = ops.workspace(dev, lib.setok_splice_workspace_bytes(B, L, L + int(rows.shape[0])), "splice")
+    # phase 1 needs the three plan slices only (the workspace query for out_cap = 1)
+    plan_bytes = lib.setok_splice_workspace_bytes(B, L, 1)
+    ws_plan = ops.workspace(dev, plan_bytes, "splice_plan")
     with torch.cuda.device(dev):
         st = lib.setok_splice_plan(ids.data_ptr(), ops._p(mask8), B, L, offsets.data_ptr(), n_images, int(tokenizer_model_max_length or 0), limit,
-                                   lens.data_ptr(), max_len.data_ptr(), ws.data_ptr(), ws.numel(), ops._stream(dev))
+                                   lens.data_ptr(), max_len.data_ptr(), ws_plan.data_ptr(), ws_plan.numel(), ops._stream(dev))
     _lib.check(st, "setok_splice_plan")
-    T = max(int(max_len.item()), 1)                            # the one host read: the reference's max(x.shape[0] ...) (:313)
+    # the one host read: the reference's max(x.shape[0] ...) (:313), together with the live row count of the ragged batch
+    T, live = (int(v) for v in torch.cat([max_len, offsets[-1:]]).tolist())
+    T = max(T, 1)
+    # only the live rows are cast / copied (a tokenizer-produced RaggedTokens has B*N rows of capacity)
+    rows = rows[:live].to(device=dev, dtype=dtype).contiguous()
+    if rows.shape[0] == 0:
+        rows = weight.new_zeros(1, weight.shape[1])
+    # phase 2: exactly-sized workspace (4 bytes per output column); the plan is carried over in its first slices
+    ws = ops.workspace(dev, lib.setok_splice_workspace_bytes(B, L, T), "splice")
+    ws[:plan_bytes].copy_(ws_plan[:plan_bytes])
     embeds = torch.empty(B, T, H, dtype=dtype, device=dev)
     labels_out = torch.empty(B, T, dtype=torch.int64, device=dev)
     mask_out = torch.empty(B, T, dtype=torch.uint8, device=dev)

@@ -31,6 +31,7 @@ import torch.nn as nn
 
 from . import _lib, ops
 from ._lib import SetokError
+from ._pack import PackedParams, stamp
 from .ragged import RaggedTokens
 
 
@@ -119,7 +120,7 @@ def _bf16(t: torch.Tensor, dev) -> torch.Tensor:
     return t.detach().to(device=dev, dtype=torch.bfloat16).contiguous()
 
 
-class CLIPVisionTower(nn.Module):
+class CLIPVisionTower(PackedParams, nn.Module):
     """Frozen CLIP-style ViT behind the reference wrapper's interface (clip_encoder.py:8-93).
 
     ``vision_tower`` is a checkpoint name/path for ``transformers`` (as in the reference) or, when no
@@ -129,9 +130,11 @@ class CLIPVisionTower(nn.Module):
 
     def __init__(self, vision_tower: Optional[str], unfreeze_mm_vision_tower: Optional[bool] = False,
                  mm_vision_select_feature: Optional[str] = "patch", mm_vision_select_layer: Optional[int] = -2,
-                 delay_load=False, vision_config=None):
+                 delay_load=False, vision_config=None, residual_f32: bool = True):
         super().__init__()
         self.is_loaded = False
+        # residual stream of the tower kept in float32 between layers (SETOK_VIT_RESIDUAL_F32); False = bf16 stream
+        self.residual_f32 = bool(residual_f32)
         self.vision_tower_name = vision_tower
         self.select_layer = mm_vision_select_layer
         self.select_feature = mm_vision_select_feature
@@ -174,17 +177,9 @@ class CLIPVisionTower(nn.Module):
         self.is_loaded = True
         self._packed = None
 
-    # -- nn.Module plumbing: any dtype/device move or weight load invalidates the packed copy
-    def _apply(self, fn, *a, **k):
-        self._packed = None
-        return super()._apply(fn, *a, **k)
-
-    def load_state_dict(self, *a, **k):
-        self._packed = None
-        return super().load_state_dict(*a, **k)
-
-    def invalidate(self):
-        self._packed = None
+    # -- the packed copy is validated against the live parameters before every forward (setok_b200/_pack.py)
+    def _pack_sources(self):
+        return (self.vision_tower,)
 
     def _pack(self):
         cfg = self.config
@@ -196,8 +191,17 @@ class CLIPVisionTower(nn.Module):
         Cc, p = cfg.hidden_size, cfg.patch_size
         Kp = (3 * p * p + 63) // 64 * 64
         keep: Dict[str, torch.Tensor] = {}
-        wp = torch.zeros(Cc, Kp, dtype=torch.bfloat16, device=dev)
-        wp[:, :3 * p * p] = _bf16(sd[pre + "embeddings.patch_embedding.weight"].reshape(Cc, -1), dev)
+        w32 = _f32(sd[pre + "embeddings.patch_embedding.weight"].reshape(Cc, -1), dev)
+        if self.residual_f32:
+            # high-precision mode: [w_hi | w_hi | w_lo] for the 3-term split patch embedding (SETOK_VIT_PATCH_SPLIT)
+            wp = torch.zeros(Cc, 3 * Kp, dtype=torch.bfloat16, device=dev)
+            w_hi = w32.to(torch.bfloat16)
+            wp[:, :3 * p * p] = w_hi
+            wp[:, Kp:Kp + 3 * p * p] = w_hi
+            wp[:, 2 * Kp:2 * Kp + 3 * p * p] = (w32 - w_hi.float()).to(torch.bfloat16)
+        else:
+            wp = torch.zeros(Cc, Kp, dtype=torch.bfloat16, device=dev)
+            wp[:, :3 * p * p] = w32.to(torch.bfloat16)
         keep["w_patch"] = wp
         keep["cls"] = _f32(sd[pre + "embeddings.class_embedding"], dev)
         keep["pos"] = _f32(sd[pre + "embeddings.position_embedding.weight"], dev)
@@ -222,7 +226,7 @@ class CLIPVisionTower(nn.Module):
         vit = _lib.Vit(image_size=cfg.image_size, patch=p, hidden=Cc, heads=cfg.num_attention_heads, layers=L,
                        mlp=cfg.intermediate_size, ln_eps=float(cfg.layer_norm_eps), w_patch=wp.data_ptr(),
                        cls=keep["cls"].data_ptr(), pos=keep["pos"].data_ptr(), pre_ln_g=keep["pre_g"].data_ptr(),
-                       pre_ln_b=keep["pre_b"].data_ptr(), layer=layers)
+                       pre_ln_b=keep["pre_b"].data_ptr(), layer=layers, flags=(_lib.VIT_RESIDUAL_F32 | _lib.VIT_PATCH_SPLIT) if self.residual_f32 else 0)
         self._packed = (vit, layers, keep)
         self._resized = {}
         return self._packed
@@ -231,7 +235,7 @@ class CLIPVisionTower(nn.Module):
         """The packed tower for `size`^2 inputs.  Other than the native size needs `interpolate_pos_encoding`: the position
         table is resized once per size exactly as HF does (bicubic on the patch grid, class row kept;
         modeling_clip.py:160-196) and cached; all kernels take the grid size as a run-time argument."""
-        vit, layers, keep = self._packed or self._pack()
+        vit, layers, keep = self._packed_get()
         if size == vit.image_size:
             return vit
         hit = self._resized.get(size)
@@ -246,7 +250,7 @@ class CLIPVisionTower(nn.Module):
             new_pos = torch.cat([pos[:1], grid.permute(0, 2, 3, 1).reshape(ng * ng, -1)], 0).contiguous().to(keep["pos"].device)
             v2 = _lib.Vit(image_size=size, patch=vit.patch, hidden=vit.hidden, heads=vit.heads, layers=vit.layers, mlp=vit.mlp,
                           ln_eps=vit.ln_eps, w_patch=vit.w_patch, cls=vit.cls, pos=new_pos.data_ptr(), pre_ln_g=vit.pre_ln_g,
-                          pre_ln_b=vit.pre_ln_b, layer=layers)
+                          pre_ln_b=vit.pre_ln_b, layer=layers, flags=vit.flags)
             hit = (v2, new_pos)
             self._resized[size] = hit
         return hit[0]
@@ -285,7 +289,7 @@ class CLIPVisionTower(nn.Module):
             return [self.forward(im.unsqueeze(0), interpolate_pos_encoding, pos_embedding) for im in images]
         if not self.is_loaded:
             raise SetokError("vision tower not loaded: call load_model() first")
-        vit, _, _ = self._packed or self._pack()
+        vit, _, _ = self._packed_get()
         dev = self.device
         if images.dim() != 4 or images.shape[1] != 3:
             raise SetokError(f"images must be (B, 3, H, W); got {tuple(images.shape)}")
@@ -383,7 +387,7 @@ def _default_image_processor(cfg):
 # --------------------------------------------------------------------------------------------
 # tokenizer
 # --------------------------------------------------------------------------------------------
-class SetokTokenizer(nn.Module):
+class SetokTokenizer(PackedParams, nn.Module):
     def __init__(self, vision_tower: str = "google/siglip-so400m-patch14-384", unfreeze_mm_vision_tower: Optional[bool] = False,
                  mm_vision_select_feature: Optional[str] = "patch", mm_vision_select_layer: Optional[int] = -2,
                  delay_load: Optional[bool] = False, hidden_dim: Optional[int] = 4096, token_feat_dim: Optional[int] = 4096,
@@ -408,9 +412,9 @@ class SetokTokenizer(nn.Module):
         self.image_feature_encoder = CLIPVisionTower(vision_tower, unfreeze_mm_vision_tower=unfreeze_mm_vision_tower,
                                                      mm_vision_select_feature=mm_vision_select_feature,
                                                      mm_vision_select_layer=mm_vision_select_layer, delay_load=delay_load,
-                                                     vision_config=kwargs.get("vision_config"))
+                                                     vision_config=kwargs.get("vision_config"),
+                                                     residual_f32=kwargs.get("tower_residual_f32", True))
         self.image_processor = self.image_feature_encoder.image_processor
-        self._packed_head = None
         self.eval()
 
     # -- reference surface -------------------------------------------------------------------
@@ -444,18 +448,13 @@ class SetokTokenizer(nn.Module):
         self.image_feature_encoder.load_model(device_map=device_map)
         self.image_processor = self.image_feature_encoder.image_processor
 
-    def _apply(self, fn, *a, **k):
-        self._packed_head = None
-        return super()._apply(fn, *a, **k)
-
-    def load_state_dict(self, *a, **k):
-        self._packed_head = None
-        self.image_feature_encoder.invalidate()
-        return super().load_state_dict(*a, **k)
+    def _pack_sources(self):
+        return (self.inner_encoder, self.inter_encoder, self.out)
 
     def invalidate(self):
-        """Call after mutating parameters in place (e.g. an optimizer step) so they are re-packed."""
-        self._packed_head = None
+        """Forces a re-pack of the kernels' parameter copies.  Not needed after ordinary in-place updates, ``.to()`` or any
+        ``load_state_dict`` (the copies are validated against the parameters' version counters before every forward)."""
+        self._packed = None
         self.image_feature_encoder.invalidate()
 
     # -- packing -----------------------------------------------------------------------------
@@ -485,8 +484,8 @@ class SetokTokenizer(nn.Module):
         keep["w_out"], keep["b_out"] = _bf16(self.out.weight, dev), _f32(self.out.bias, dev)
         head = _lib.Head(hidden=self.hidden_dim, heads=self.nheads, mlp=self.dim_feedforward, token_dim=self.token_feat_dim,
                          inner=inner, inter=inter, w_out=keep["w_out"].data_ptr(), b_out=keep["b_out"].data_ptr())
-        self._packed_head = (head, keep)
-        return self._packed_head
+        self._packed = (head, keep)
+        return self._packed
 
     # -- forward -----------------------------------------------------------------------------
     @torch.no_grad()
@@ -495,7 +494,7 @@ class SetokTokenizer(nn.Module):
         """The head of tokenizer.py:162-182 for a batch of tower features (B, N, C).  Returns
         (RaggedTokens, idx_cluster (B, N) int64, score (B, 1, N)).  ``embedded``: `feats` is already
         ``features + pos`` in float32 (``image_feature_encoder(images, pos_embedding=...)``)."""
-        head, _ = self._packed_head or self._pack()
+        head, _ = self._packed_get()
         dev = self.device
         if feats.dim() == 2:
             feats = feats.unsqueeze(0)
@@ -543,7 +542,8 @@ class SetokTokenizer(nn.Module):
         return rt, idx, score.unsqueeze(1)
 
     @torch.no_grad()
-    def forward(self, x, k=None, threshold=None, token_mask=None, noise=None, interpolate_pos_encoding: bool = False):
+    def forward(self, x, k=None, threshold=None, token_mask=None, noise=None, interpolate_pos_encoding: bool = False,
+                token_dtype: Optional[torch.dtype] = None):
         """x: images (B, 3, H, W) (or a list of (3, H, W)).  Returns the reference's 3-tuple
         ``(group_features, idx_cluster, score)`` (tokenizer.py:182) for the whole batch: ``group_features`` is a
         RaggedTokens whose ``[b]`` is image b's (K_b, C_tok) tensor, ``idx_cluster`` is (B, N) int64 and
@@ -553,7 +553,7 @@ class SetokTokenizer(nn.Module):
         processed as one batch per resolution and re-packed in the original image order; ``idx_cluster`` / ``score``
         are then per-image lists because N differs, and ``noise`` is a list of (N_i,) tensors."""
         if isinstance(x, (list, tuple)) and len({tuple(im.shape) for im in x}) > 1:
-            return self._forward_mixed(list(x), k, threshold, noise, interpolate_pos_encoding)
+            return self._forward_mixed(list(x), k, threshold, noise, interpolate_pos_encoding, token_mask, token_dtype)
         if isinstance(x, (list, tuple)):
             x = torch.stack(list(x), dim=0)
             if isinstance(noise, (list, tuple)):
@@ -562,13 +562,15 @@ class SetokTokenizer(nn.Module):
         if tower.select_feature == "patch" and torch.is_tensor(x):
             # a1..a3 in one call: the tower's last row pass drops CLS and adds the position embedding (tokenizer.py:164-169)
             x_pos = tower(x, interpolate_pos_encoding, pos_embedding=self.position_embedding)
-            token_dtype = torch.bfloat16 if x.dtype == torch.bfloat16 else torch.float32
+            token_dtype = token_dtype or (torch.bfloat16 if x.dtype == torch.bfloat16 else torch.float32)
             return self.encode_features(x_pos, k=k, threshold=threshold, token_mask=token_mask, noise=noise, token_dtype=token_dtype,
                                         embedded=True)
         feats = tower(x, interpolate_pos_encoding)
-        return self.encode_features(feats, k=k, threshold=threshold, token_mask=token_mask, noise=noise)
+        return self.encode_features(feats, k=k, threshold=threshold, token_mask=token_mask, noise=noise, token_dtype=token_dtype)
 
-    def _forward_mixed(self, images, k, threshold, noise, interpolate_pos_encoding):
+    def _forward_mixed(self, images, k, threshold, noise, interpolate_pos_encoding, token_mask=None, token_dtype=None):
+        if token_mask is not None and (not isinstance(token_mask, (list, tuple)) or len(token_mask) != len(images)):
+            raise SetokError("a mixed-resolution batch takes token_mask as a list with one (N_i,) mask per image")
         groups: Dict[tuple, List[int]] = {}
         for i, im in enumerate(images):
             groups.setdefault(tuple(im.shape), []).append(i)
@@ -579,7 +581,9 @@ class SetokTokenizer(nn.Module):
         for shape, members in groups.items():
             batch = torch.stack([images[i] for i in members], dim=0)
             nz = None if noise is None else torch.stack([noise[i] for i in members], dim=0)
-            rt, idx, score = self.forward(batch, k=k, threshold=threshold, noise=nz, interpolate_pos_encoding=interpolate_pos_encoding)
+            tm = None if token_mask is None else torch.stack([token_mask[i].reshape(-1) for i in members], dim=0)
+            rt, idx, score = self.forward(batch, k=k, threshold=threshold, token_mask=tm, noise=nz,
+                                          interpolate_pos_encoding=interpolate_pos_encoding, token_dtype=token_dtype)
             for j, i in enumerate(members):
                 per_tokens[i], idxs[i], scores[i] = rt[j], idx[j], score[j]
         counts = torch.tensor([0] + [t.shape[0] for t in per_tokens], dtype=torch.int32)

@@ -1,4 +1,6 @@
-"""CPU, world_size 2 over gloo: the ragged all-gather that repacks per-rank token outputs."""
+"""CPU, world_size 2 over gloo: the ragged all-gather that repacks per-rank token outputs -- equal and
+unequal per-rank image counts, the dealt (`deal_by_cost`) order restored, `index_down` carried along, and the two-phase
+(start / finish) form the streaming pipeline uses."""
 import os
 import socket
 
@@ -12,18 +14,41 @@ def _free_port():
     return p
 
 
+def _ragged(counts, rank, width=3, cap_extra=4, down_n=0):
+    from setok_b200 import RaggedTokens
+    total = sum(counts)
+    data = torch.zeros(total + cap_extra, width)                      # capacity > live rows
+    data[:total] = torch.arange(total * width, dtype=torch.float32).reshape(total, width) + 100 * rank
+    offs = torch.tensor([0] + list(torch.tensor(counts).cumsum(0)) if counts else [0], dtype=torch.int32)
+    down = None
+    if down_n:
+        down = torch.full((len(counts), down_n), -1, dtype=torch.int64)
+        for i, c in enumerate(counts):
+            down[i, :c] = torch.arange(c) + 10 * i + 1000 * rank
+    return RaggedTokens(data, offs, down)
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from setok_b200 import RaggedTokens
-    from setok_b200.dist import all_gather_ragged
-    counts = [[2, 0, 5], [1, 4, 1]][rank]
-    total = sum(counts)
-    data = torch.zeros(12, 3)                       # capacity 12 rows, `total` live
-    data[:total] = torch.arange(total * 3, dtype=torch.float32).reshape(total, 3) + 100 * rank
-    offs = torch.tensor([0] + list(torch.tensor(counts).cumsum(0)), dtype=torch.int32)
-    out = all_gather_ragged(RaggedTokens(data, offs))
-    q.put((rank, out.counts, out.packed().clone()))
+    from setok_b200.dist import RaggedAllGather, all_gather_ragged
+    res = {}
+    # (a) equal B, blocking form
+    out = all_gather_ragged(_ragged([[2, 0, 5], [1, 4, 1]][rank], rank))
+    res["equal"] = (out.counts, out.packed().clone())
+    # (b) unequal B (3 vs 1 images), index_down carried, order given by a dealing of 4 images: rank 0 holds global images
+    #     {0, 2, 3}, rank 1 holds {1}
+    counts = [[2, 3, 1], [4]][rank]
+    order = [[0, 2, 3], [1]][rank]
+    out = all_gather_ragged(_ragged(counts, rank, down_n=6), order=order)
+    res["unequal"] = (out.counts, out.packed().clone(), out.index_down.clone())
+    # (c) two-phase form with a fixed batch capacity, two batches in flight, one rank with an empty batch of rows
+    g = RaggedAllGather(batch_capacity=4)
+    h1 = g.start(_ragged([[1, 1], [0, 0, 2]][rank], rank))
+    h2 = g.start(_ragged([[3], [1, 1]][rank], rank + 2))
+    o1, o2 = g.finish(h1), g.finish(h2)
+    res["two_phase"] = (o1.counts, o1.packed().clone(), o2.counts, o2.packed().clone())
+    q.put((rank, res))
     dist.destroy_process_group()
 
 
@@ -33,13 +58,24 @@ def test_all_gather_ragged_world2():
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     [p.start() for p in procs]
-    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    res = sorted([q.get(timeout=180) for _ in procs], key=lambda t: t[0])
     [p.join(60) for p in procs]
-    exp0 = torch.arange(21, dtype=torch.float32).reshape(7, 3)
-    exp1 = torch.arange(18, dtype=torch.float32).reshape(6, 3) + 100
-    for rank, counts, packed in res:
+    rows = lambda n, base: torch.arange(n * 3, dtype=torch.float32).reshape(n, 3) + base
+    for rank, r in res:
+        counts, packed = r["equal"]
         assert counts == [2, 0, 5, 1, 4, 1]
-        assert torch.equal(packed, torch.cat([exp0, exp1]))
+        assert torch.equal(packed, torch.cat([rows(7, 0), rows(6, 100)]))
+        # dealt order restored: global images 0, 1, 2, 3 = rank0[0], rank1[0], rank0[1], rank0[2]
+        counts, packed, down = r["unequal"]
+        assert counts == [2, 4, 3, 1]
+        r0, r1 = rows(6, 0), rows(4, 100)
+        assert torch.equal(packed, torch.cat([r0[0:2], r1, r0[2:5], r0[5:6]]))
+        assert down.shape == (4, 6)
+        assert down[0, :2].tolist() == [0, 1] and down[1, :4].tolist() == [1000, 1001, 1002, 1003]
+        assert down[2, :3].tolist() == [10, 11, 12] and down[3, :2].tolist() == [20, -1]
+        c1, p1, c2, p2 = r["two_phase"]
+        assert c1 == [1, 1, 0, 0, 2] and torch.equal(p1, torch.cat([rows(2, 0), rows(2, 100)]))
+        assert c2 == [3, 1, 1] and torch.equal(p2, torch.cat([rows(3, 200), rows(2, 300)]))
 
 
 def test_deal_by_cost_balances_mixed_resolutions():
