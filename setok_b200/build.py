@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsetok_b200.so")
-SOURCES = ["core.cu", "gemm_tcgen05.cu", "attention.cu", "attention_tcgen05.cu", "rowops.cu", "dpc.cu", "dpc_fused.cu", "splice.cu", "api.cu"]
+SOURCES = ["core.cu", "gemm_tcgen05.cu", "attention.cu", "attention_tcgen05.cu", "attention_fullrow.cu", "rowops.cu", "dpc.cu", "dpc_fused.cu", "splice.cu", "api.cu"]
 HEADERS = ["common.cuh", "rowops.cuh", os.path.join("..", "..", "include", "setok_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
@@ -34,11 +34,12 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+    if not force and not _stale() and not os.environ.get("SETOK_BUILD_OUT"):
         return LIB
     nvcc = _nvcc()
     extra = os.environ.get("SETOK_NVCC_EXTRA", "").split()     # e.g. -DSETOK_ATTN_TRACE for tools/attn_timeline.py
-    objdir = os.path.join(HERE, "build")
+    out_lib = os.environ.get("SETOK_BUILD_OUT") or LIB          # A/B and trace builds go elsewhere (load with SETOK_B200_LIB)
+    objdir = os.path.join(HERE, "build" if out_lib == LIB else "build_" + os.path.basename(out_lib).replace(".", "_"))
     os.makedirs(objdir, exist_ok=True)
     procs = []
     for s in SOURCES:
@@ -53,12 +54,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {s}")
         objs.append(obj)
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-lcudart"]
+    cmd = [nvcc, "-shared", "-o", out_lib, *objs, "-lcudart"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)
         raise RuntimeError("link failed")
-    return LIB
+    return out_lib
 
 
 if __name__ == "__main__":

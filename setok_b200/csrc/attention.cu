@@ -240,8 +240,11 @@ int launch_attention(const void* qkv, void* out, int rows, int C, int heads, flo
   } else {
     SETOK_REQUIRE(seg_off && row_seg, SETOK_ERR_BAD_ARG, "attention: seg_off/row_seg required for ragged segments");
   }
-  if (uniform_T > 0 && hd == 64 && m_dev == nullptr)
+  if (uniform_T > 0 && hd == 64 && m_dev == nullptr) {
+    // T <= 257 (the 224^2 tower and shorter): whole score rows in tensor memory; longer sequences: 64-key chunks, online softmax
+    if (attention_fullrow_supported(uniform_T)) return launch_attention_fullrow(qkv, out, rows / uniform_T, uniform_T, C, heads, scale, stream);
     return launch_attention_tcgen05(qkv, out, rows / uniform_T, uniform_T, C, heads, scale, stream);
+  }
   const long long warps = static_cast<long long>(rows) * heads;
   long long blocks = (warps + 7) / 8;
   const long long cap = static_cast<long long>(num_sms()) * 32;

@@ -290,6 +290,18 @@ __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_
         "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+// one fp32 column of 32 lanes
+__device__ __forceinline__ uint32_t tmem_ld_32x32b_x1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+  return r;
+}
+// 32 lanes x 8 consecutive columns, registers -> TMEM
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // generic-proxy smem writes -> visible to the async proxy (UMMA / TMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -415,6 +427,8 @@ int launch_dpc_fused(const void* feats, int feat_dtype, const float* pos, const 
 int launch_layernorm(const void* in, int in_dtype, void* out, int out_dtype, const float* gamma, const float* beta,
                      float eps, int rows, int C, const int32_t* gather, const int32_t* m_dev, cudaStream_t stream);
 int launch_attention_tcgen05(const void* qkv, void* out, int B, int T, int C, int heads, float scale, cudaStream_t stream);
+bool attention_fullrow_supported(int T);
+int launch_attention_fullrow(const void* qkv, void* out, int B, int T, int C, int heads, float scale, cudaStream_t stream);
 int launch_attention(const void* qkv, void* out, int rows, int C, int heads, float scale, const int32_t* seg_off,
                      const int32_t* row_seg, int uniform_T, const int32_t* m_dev, cudaStream_t stream);
 int launch_cross_attention(const void* q, const void* kv, void* out, int rows, int Q, int C, int heads, float scale,

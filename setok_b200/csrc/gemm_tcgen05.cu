@@ -53,6 +53,8 @@ struct GemmDev {
   long long d_batch_stride;   // elements of D's type
   long long r_batch_stride;   // elements of the residual's type
   int w_mn_major;
+  int epi_mode;               // debug (setok_debug_set_gemm_epi_mode): 0 normal; 1 drain only (no transpose / math / stores);
+                              // 2 transpose + math, no residual loads / stores; 3 normal minus the residual loads
 };
 
 // Epilogue configuration is a template so the per-element code has no run-time branches; -1 = run time
@@ -220,7 +222,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
         }
       };
-      if (PF > 0) {
+      const int epi_mode = p.epi_mode;
+      if (PF > 0 && epi_mode == 0) {
 #pragma unroll
         for (int ch = 0; ch < PF; ++ch) prefetch(ch, ch);
       }
@@ -236,7 +239,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         if (PF > 0) {
 #pragma unroll
           for (int it = 0; it < 8; ++it) { if (RES == 1) rb[it] = rt[ch % PF][it]; else rf[it] = rtf[ch % PF][it]; }
-          if (PF < 4 && ch + PF < 4) prefetch(ch + PF, ch % PF);
+          if (PF < 4 && ch + PF < 4 && epi_mode == 0) prefetch(ch + PF, ch % PF);
         } else if (res_kind == 1) {
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
@@ -268,6 +271,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         uint32_t r0[32];
         tmem_ld_32x32b_x32(taddr + ch * 32, r0);
         tmem_ld_wait();
+        if (epi_mode == 1) continue;
         // transpose through smem: thread `lane` owns tile row q*32+lane, 32 fp32 columns (8 x 16 B, XOR-swizzled)
 #pragma unroll
         for (int c = 0; c < 8; ++c)
@@ -291,6 +295,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           } else if (res_kind == 2) {
             v.x += rf[it].x; v.y += rf[it].y; v.z += rf[it].z; v.w += rf[it].w;
           }
+          if (epi_mode == 2) { if (v.x == 1.2345e30f) p.act = 0; continue; }   // keep the math alive, store nothing
           if (grow < M_eff && col_ok) {
             const long long orow = remap_P > 0 ? (grow + grow / remap_P + 1) : grow;
             if (out_f32) {
@@ -359,6 +364,7 @@ int make_tmap_bf16(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t col
 
 }  // namespace
 
+int g_gemm_epi_mode = 0;
 int g_gemm_cta_group = 0;   // 0 = automatic; 1 forces single-CTA tiles (debug / A-B timing via setok_debug_set_gemm_cta_group)
 
 int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
@@ -417,6 +423,7 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   p.res_kind = res_kind;
   p.remap_P = g.remap_P;
   p.batch = g.batch; p.d_batch_stride = g.d_batch_stride; p.r_batch_stride = g.r_batch_stride; p.w_mn_major = g.w_mn_major;
+  p.epi_mode = g_gemm_epi_mode;
   const int tiles = ceil_div(g.M, BM * cg) * ceil_div(g.N, BN) * g.batch;
   const int max_groups = num_sms() / cg;
   const int grid = (tiles < max_groups ? tiles : max_groups) * cg;
@@ -456,3 +463,4 @@ extern "C" int setok_gemm_bf16_batched(const void* A, int64_t lda, int64_t a_bat
 }
 
 extern "C" void setok_debug_set_gemm_cta_group(int cg) { setok::g_gemm_cta_group = cg; }
+extern "C" void setok_debug_set_gemm_epi_mode(int mode) { setok::g_gemm_epi_mode = mode; }

@@ -42,3 +42,21 @@ def mog_features(B: int, N: int, C: int, seed: int, device="cpu", g_min: int = 8
     lab = (torch.rand(B, N, generator=gen, device=dev) * G[:, None]).long()
     x = torch.gather(centres, 1, lab[..., None].expand(B, N, C))
     return x + sigma * torch.randn(B, N, C, generator=gen, device=dev)
+
+
+def mondrian_u8(B: int, size: int, seed: int, g_min: int = 8, g_max: int = 128) -> torch.Tensor:
+    """The same "Mondrian" images as raw uint8 pixels (B, 3, size, size) on the host: what an image decoder hands to the
+    processor.  `normalize_u8` gives the float32 tensor CLIPImageProcessor.rescale + normalize makes of them."""
+    x = mondrian_images(B, size, seed, "cpu", g_min, g_max)
+    mean = torch.tensor(CLIP_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(CLIP_STD).view(1, 3, 1, 1)
+    return (x * std + mean).clamp_(0.0, 1.0).mul_(255.0).round_().to(torch.uint8).contiguous()
+
+
+def normalize_u8(u8: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
+    """float32(float64(u8) / 255) then (x - mean) / std in float32: transformers' CLIPImageProcessor arithmetic, the same
+    values `CLIPVisionTower.forward(uint8)` computes on the device."""
+    lut = (torch.arange(256, dtype=torch.float64) * (1.0 / 255.0)).to(torch.float32)
+    mean = torch.tensor(CLIP_MEAN, dtype=torch.float32).view(1, 3, 1, 1)
+    std = torch.tensor(CLIP_STD, dtype=torch.float32).view(1, 3, 1, 1)
+    return ((lut[u8.long()] - mean) / std).to(dtype).contiguous()

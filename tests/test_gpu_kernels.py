@@ -147,7 +147,12 @@ def test_attention_ragged_segments(C, heads):
     assert torch.equal(out2[:138], out[:138])
 
 
-@pytest.mark.parametrize("T,B,heads", [(17, 3, 2), (64, 2, 4), (82, 2, 2), (197, 2, 12), (257, 3, 16), (577, 1, 16)])
+@pytest.mark.parametrize("T,B,heads", [(17, 3, 2), (64, 2, 4), (82, 2, 2), (197, 2, 12), (257, 3, 16), (577, 1, 16),
+                                       # T <= 257 runs the whole-row kernel (attention_fullrow.cu): one / two query tiles, key counts that
+                                       # are not multiples of 16 or 64, the 257th key + query row, and more (image, head) pairs than SMs so
+                                       # that every persistent CTA walks several pairs through its 2-stage ring (barrier parities wrap)
+                                       (1, 4, 2), (16, 5, 2), (128, 10, 16), (129, 10, 16), (256, 10, 16), (197, 30, 12), (257, 20, 16), (257, 40, 16),
+                                       (1025, 1, 2)])
 def test_attention_vit_hd64(T, B, heads):
     C = heads * 64
     g = torch.Generator().manual_seed(T)
