@@ -118,10 +118,21 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # synthetic inputs: generated on the HOST once, so that the CPU arm and the GPU arm consume the same tensors
 # ------------------------------------------------------------------------------------------------
+_HOST_BATCHES = {}
+
+
 def host_batch(config: int, rank: int, n: int = None):
-    """(uint8 pixels, float images, noise) of one rank's batch.  The float images are the processor's output for the uint8
-    pixels (rescale + normalize), so the uint8 end-to-end path and the float paths see identical pixels.  Config 5 returns
-    lists (one entry per image, three resolutions)."""
+    """(uint8 pixels, float images, noise) of one rank's batch, generated once per process (the CPU arm takes a prefix of
+    the very tensors the GPU arm uploads).  The float images are the processor's output for the uint8 pixels (rescale +
+    normalize), so the uint8 end-to-end path and the float paths see identical pixels.  Config 5 returns lists (one entry
+    per image, three resolutions)."""
+    key = (config, rank, n)
+    if key not in _HOST_BATCHES:
+        _HOST_BATCHES[key] = _make_host_batch(config, rank, n)
+    return _HOST_BATCHES[key]
+
+
+def _make_host_batch(config: int, rank: int, n: int = None):
     from setok_b200.synth import mondrian_u8, normalize_u8
     B = n or BATCHES[config]
     if config == 5:
@@ -154,7 +165,7 @@ class CpuOracle:
         self.size = size
         self.tp = O.make_tower_params(C, VIT["num_hidden_layers"], VIT["num_attention_heads"], VIT["patch_size"], size if config == 3 else 224, seed=0)
         self.hp = O.make_head_params(C, HEAD["token_feat_dim"], HEAD["dim_feedforward"], seed=0)
-        _, self.imgs, self.noise = host_batch(config, 0, max_images if config != 5 else max(3, max_images))
+        _, self.imgs, self.noise = host_batch(config, 0)      # rank 0's full batch; run(n) takes its first n images
         self.kw = dict(patch=14, heads=16, layers=24, select_layer=-2)
         if config == 3:
             from oracle import detok_oracle as D
@@ -319,7 +330,7 @@ def gpu_eager_baseline(dev, tok, images, noise, head_sample=16):
     n = min(head_sample, images.shape[0])
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    with torch.no_grad():
+    with torch.no_grad(), torch.device(dev):                      # the oracle's factory calls (arange, zeros ...) land on the device
         for b in range(n):
             O.tokenizer_head(feats[b], noise[b], hp, min_cluster_num=64, threshold=0.5, k=KNN_K)
     torch.cuda.synchronize()

@@ -300,6 +300,35 @@ int setok_splice(const int64_t* input_ids, const uint8_t* attention_mask, const 
                  uint8_t* mask_out, int64_t* pos_out, int32_t* lens, int32_t* max_len, void* workspace,
                  size_t workspace_bytes, setok_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * image preprocessing on the device.  Replaces, for a whole batch of decoded images of arbitrary sizes,
+ * what the reference does per image on the host: process_images / expand2square (src/mm_utils.py:152-182) followed by
+ * CLIPImageProcessor.preprocess of transformers 4.46.3 (PIL bicubic resize of the uint8 image to the shortest edge, center
+ * crop); rescale + normalize then happen inside setok_vit_forward_u8.  Integer arithmetic (Pillow's 22-bit fixed-point
+ * resampling, restated), bit-exact against PIL.
+ *   One descriptor per image.  The host builds the tap tables exactly as Pillow's precompute_coeffs does (double precision,
+ *   then fixed point): per axis, S rows of [first source index, tap count, taps[ksize]] for the S output pixels that survive
+ *   the crop.  `canvas` = the image after the optional pad-to-square: the source pasted at (pad_x, pad_y) into an Hp x Wp
+ *   background-coloured rectangle (never materialised).
+ */
+typedef struct {
+  const uint8_t* src;          /* (device) H x W x 3 uint8, HWC, as decoded */
+  int H, W;
+  int pad_x, pad_y;            /* where the source sits in the canvas (0, 0 without padding) */
+  int y0, y1;                  /* canvas rows [y0, y1) the vertical pass reads (the horizontal pass computes only those) */
+  int top, left;               /* crop origin in the resized image (used by the identity passes) */
+  int identity_x, identity_y;  /* the pass does not change the size: Pillow skips it */
+  int ksize_x, ksize_y;        /* taps per table row */
+  int kx_off, ky_off;          /* offsets (int32 words) of this image's horizontal / vertical tables in `tables` */
+  long long tmp_off;           /* offset (bytes) of this image's [(y1 - y0), S, 3] intermediate in the workspace */
+} setok_resize_desc;
+
+/* descs (device) [B]; max_rows = max_b (y1 - y0); tables (device) int32; background: the pad colour (host, 3 bytes);
+ * out (device) uint8 [B, 3, S, S]; workspace_needed = sum_b (y1 - y0) * S * 3 (the caller knows it from the descriptors). */
+int setok_preprocess_u8(const setok_resize_desc* descs, int B, int max_rows, const int32_t* tables, int S,
+                        const uint8_t* background, uint8_t* out, void* workspace, size_t workspace_bytes,
+                        size_t workspace_needed, setok_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

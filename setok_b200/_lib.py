@@ -75,6 +75,12 @@ class Detok(C.Structure):
                 ("block", C.POINTER(VitLayer)), ("norm_g", c_void_p), ("norm_b", c_void_p)]
 
 
+class ResizeDesc(C.Structure):
+    _fields_ = [("src", c_void_p), ("H", c_int), ("W", c_int), ("pad_x", c_int), ("pad_y", c_int), ("y0", c_int), ("y1", c_int), ("top", c_int),
+                ("left", c_int), ("identity_x", c_int), ("identity_y", c_int), ("ksize_x", c_int), ("ksize_y", c_int), ("kx_off", c_int),
+                ("ky_off", c_int), ("tmp_off", C.c_longlong)]
+
+
 # name -> (restype, argtypes); every symbol include/setok_b200.h declares
 SIGNATURES = {
     "setok_last_error": (C.c_char_p, []),
@@ -109,6 +115,7 @@ SIGNATURES = {
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "setok_splice": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "setok_preprocess_u8": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_void_p]),
     "setok_project_workspace_bytes": (c_size_t, [C.POINTER(Projector), c_int]),
     "setok_project": (c_int, [C.POINTER(Projector), c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
 }

@@ -22,7 +22,10 @@
 #include "common.cuh"
 
 namespace setok {
-int g_attn_fullrow = 1;   // 0: always the chunked kernel (A/B timing via setok_debug_set_attention_fullrow)
+// 0: always the chunked kernel; 1: whole-row kernel where it wins (225 <= T <= 257: two full query tiles); 2: whole-row kernel
+// for every T <= 257 (tests, A/B timing) -- setok_debug_set_attention_fullrow
+int g_attn_fullrow = 1;
+int g_attn_fullrow_dbg = 0;   // timing experiments only (results are wrong): 1 skip pass 1, 2 no exp2, 4 no P store, 8 no O store
 namespace {
 
 constexpr int FR_THREADS = 352;
@@ -36,9 +39,10 @@ constexpr int FR_STAGES = 2;
 constexpr int FR_OFF_SLEFT = FR_STAGES * FR_STAGE_BYTES;              // float s_left[256]: scores of row 256 against keys 0..255
 constexpr int FR_PLEFT_STRIDE = 264;                                   // floats per buffer: p[0..256], inv_l at [257]
 constexpr int FR_OFF_PLEFT = FR_OFF_SLEFT + 256 * 4;                  // float p_left[2][264]
-constexpr int FR_OFF_PART = FR_OFF_PLEFT + 2 * FR_PLEFT_STRIDE * 4;   // float part[2][8][64]
-constexpr int FR_OFF_BAR = FR_OFF_PART + 2 * 8 * 64 * 4;
-constexpr int FR_NUM_BARS = 2 * FR_STAGES + 8 + 3;
+constexpr int FR_OFF_PART = FR_OFF_PLEFT + 2 * FR_PLEFT_STRIDE * 4;   // float part[8][64]
+constexpr int FR_OFF_STG = FR_OFF_PART + 8 * 64 * 4;                  // O staging: 8 warps x 16 rows x 128 B
+constexpr int FR_OFF_BAR = FR_OFF_STG + 8 * 2048;
+constexpr int FR_NUM_BARS = 4 * FR_STAGES + 10 + 3;
 constexpr int FR_SMEM_BYTES = FR_OFF_BAR + FR_NUM_BARS * 8 + 16 + 1024;
 // tensor-memory columns inside a tile's 256-column region
 constexpr uint32_t FR_COL_O = 128, FR_COL_PX = 192, FR_COL_E = 208, FR_COL_L0 = 224, FR_COL_L1 = 240;
@@ -49,10 +53,20 @@ __device__ __forceinline__ float fr_exp2(float x) {      // MUFU.EX2; exp2(-inf)
   return y;
 }
 
+#ifdef SETOK_ATTN_TRACE
+__device__ long long* g_fr_trace = nullptr;   // [3 roles][64 slots] clock64 stamps of CTA 0, local pair 2 (tools/attn_timeline.py --fullrow)
+#define FR_TRACE(role, slot) do { if (blockIdx.x == 0 && n == 2 && lane == 0 && (warp & 3) == 0 && g_fr_trace != nullptr) g_fr_trace[(role) * 64 + (slot)] = clock64(); } while (0)
+#define FR_TRACE_M(slot) do { if (blockIdx.x == 0 && n == 2 && g_fr_trace != nullptr) g_fr_trace[2 * 64 + (slot)] = clock64(); } while (0)
+#else
+#define FR_TRACE(role, slot) do { } while (0)
+#define FR_TRACE_M(slot) do { } while (0)
+#endif
+
 struct FrParams {
   bf16* out;
   int T, heads, C, n_pairs;
   float scale_log2;
+  int dbg;
 };
 
 __global__ void __launch_bounds__(FR_THREADS, 1)
@@ -75,19 +89,29 @@ attn_fullrow_hd64_kernel(const __grid_constant__ CUtensorMap tm256, const __grid
   float* p_left = reinterpret_cast<float*>(smem + FR_OFF_PLEFT);
   float* part = reinterpret_cast<float*>(smem + FR_OFF_PART);
   const uint32_t bar0 = base + FR_OFF_BAR;
-  auto qkv_full = [&](int s) { return bar0 + 8u * s; };
-  auto qkv_empty = [&](int s) { return bar0 + 8u * (FR_STAGES + s); };
-  auto s_full = [&](int t) { return bar0 + 8u * (2 * FR_STAGES + t); };
-  auto p_full = [&](int t) { return bar0 + 8u * (2 * FR_STAGES + 2 + t); };
-  auto o_full = [&](int t) { return bar0 + 8u * (2 * FR_STAGES + 4 + t); };
-  auto o_read = [&](int t) { return bar0 + 8u * (2 * FR_STAGES + 6 + t); };
-  const uint32_t left_s = bar0 + 8u * (2 * FR_STAGES + 8), left_p = left_s + 8u, left_o = left_s + 16u;
+  // Two load groups per stage with their own full / empty barriers: K + Q (+ the 257th q / k rows) are dead as soon as the
+  // pair's score MMAs have been issued, i.e. early in the pair, so the NEXT-BUT-ONE pair's K / Q are in flight almost two
+  // pairs ahead of their use; V (+ the 257th v row) lives until the pair's P.V is done and its O has been staged out.
+  auto kq_full = [&](int s) { return bar0 + 8u * s; };
+  auto kq_empty = [&](int s) { return bar0 + 8u * (FR_STAGES + s); };
+  auto v_full = [&](int s) { return bar0 + 8u * (2 * FR_STAGES + s); };
+  auto v_empty = [&](int s) { return bar0 + 8u * (3 * FR_STAGES + s); };
+  auto s_full = [&](int t) { return bar0 + 8u * (4 * FR_STAGES + t); };
+  auto p_full = [&](int t) { return bar0 + 8u * (4 * FR_STAGES + 2 + t); };
+  auto o_full = [&](int t) { return bar0 + 8u * (4 * FR_STAGES + 4 + t); };
+  auto o_read = [&](int t) { return bar0 + 8u * (4 * FR_STAGES + 6 + t); };
+  auto e_full = [&](int t) { return bar0 + 8u * (4 * FR_STAGES + 8 + t); };     // the 257th-key / row scores of the NEXT pair are in TMEM
+  const uint32_t left_s = bar0 + 8u * (4 * FR_STAGES + 10), left_p = left_s + 8u, left_o = left_s + 16u;
   volatile uint32_t* tmem_holder = reinterpret_cast<volatile uint32_t*>(smem + FR_OFF_BAR + FR_NUM_BARS * 8);
 
   if (warp == FR_W_TMA && lane == 0) {
     tma_prefetch_desc(&tm256);
     tma_prefetch_desc(&tm16);
-    for (int s = 0; s < FR_STAGES; ++s) { mbar_init(qkv_full(s), 1); mbar_init(qkv_empty(s), leftover ? 2 : 1); }
+    for (int s = 0; s < FR_STAGES; ++s) {
+      mbar_init(kq_full(s), 1); mbar_init(kq_empty(s), leftover ? 2 : 1);            // MMA commit (+ the auxiliary warp)
+      mbar_init(v_full(s), 1); mbar_init(v_empty(s), leftover ? 2 : 1);
+    }
+    for (int t = 0; t < 2; ++t) mbar_init(e_full(t), 1);
     for (int t = 0; t < 2; ++t) { mbar_init(s_full(t), 1); mbar_init(p_full(t), 4); mbar_init(o_full(t), 1); mbar_init(o_read(t), 4); }
     mbar_init(left_s, 4); mbar_init(left_p, 1); mbar_init(left_o, 8);
     fence_mbar_init();
@@ -106,90 +130,118 @@ attn_fullrow_hd64_kernel(const __grid_constant__ CUtensorMap tm256, const __grid
         const int g = static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x);
         const int b = g / p.heads, h = g % p.heads;
         const int st = n & 1;
-        mbar_wait(qkv_empty(st), (((n >> 1) & 1) ^ 1));
         const uint32_t sb = base + st * FR_STAGE_BYTES;
-        mbar_arrive_expect_tx(qkv_full(st), 3 * FR_TILE_BYTES + (leftover ? 3 * FR_X_BYTES : 0));
-        tma_load_3d(&tm256, qkv_full(st), sb + FR_OFF_K, C + h * 64, 0, b);
-        tma_load_3d(&tm256, qkv_full(st), sb + FR_OFF_Q, h * 64, 0, b);
-        tma_load_3d(&tm256, qkv_full(st), sb + FR_OFF_V, 2 * C + h * 64, 0, b);
+        const uint32_t par = ((n >> 1) & 1) ^ 1u;
+        mbar_wait(kq_empty(st), par);
+        mbar_arrive_expect_tx(kq_full(st), 2 * FR_TILE_BYTES + (leftover ? 2 * FR_X_BYTES : 0));
+        tma_load_3d(&tm256, kq_full(st), sb + FR_OFF_K, C + h * 64, 0, b);
+        tma_load_3d(&tm256, kq_full(st), sb + FR_OFF_Q, h * 64, 0, b);
         if (leftover) {
-          tma_load_3d(&tm16, qkv_full(st), sb + FR_OFF_QX, h * 64, 256, b);
-          tma_load_3d(&tm16, qkv_full(st), sb + FR_OFF_KX, C + h * 64, 256, b);
-          tma_load_3d(&tm16, qkv_full(st), sb + FR_OFF_VX, 2 * C + h * 64, 256, b);
+          tma_load_3d(&tm16, kq_full(st), sb + FR_OFF_QX, h * 64, 256, b);
+          tma_load_3d(&tm16, kq_full(st), sb + FR_OFF_KX, C + h * 64, 256, b);
         }
+        mbar_wait(v_empty(st), par);
+        mbar_arrive_expect_tx(v_full(st), FR_TILE_BYTES + (leftover ? FR_X_BYTES : 0));
+        tma_load_3d(&tm256, v_full(st), sb + FR_OFF_V, 2 * C + h * 64, 0, b);
+        if (leftover) tma_load_3d(&tm16, v_full(st), sb + FR_OFF_VX, 2 * C + h * 64, 256, b);
       }
     }
   } else if (warp == FR_W_MMA) {
     // ------------------------------------------------ MMA issuer -------------------------------------------------------
-    if (lane == 0 && n_local > 0) {
+    // The whole warp runs this role convergently (waits included) and one elected lane issues the tcgen05 instructions: with
+    // warp-uniform control flow the operand descriptors stay in uniform registers (in the in-kernel timeline a divergent
+    // single-lane issuer spent ~90 cycles per tcgen05.mma, three times the 32 cycles a 128x64x16 MMA executes in).
+    if (n_local > 0) {
       const uint32_t idesc_s = umma_idesc_bf16(128, Nk);
       const uint32_t idesc_x = umma_idesc_bf16(128, 16);
       const uint32_t idesc_pv = umma_idesc_bf16(128, 64, true);
+      const int ksteps = Nk >> 4;
       auto stage_base = [&](int n) { return base + static_cast<uint32_t>((n & 1) * FR_STAGE_BYTES); };
       // S_t(n) = Q_t K^T: 4 k-steps of 16 dims (+32 B inside the 128 B rows)
-      auto issue_s = [&](int t, int n) {
+      auto issue_s = [&](int t, int n, bool last) {
         const uint32_t sb = stage_base(n);
         const uint64_t dq = umma_desc_k_sw128(sb + FR_OFF_Q + t * 16384), dk = umma_desc_k_sw128(sb + FR_OFF_K);
         const uint32_t d = tmem_base + 256u * t;
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16(d, dq + 2 * k, dk + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-        umma_commit(s_full(t));
+          for (int k = 0; k < 4; ++k) umma_f16(d, dq + 2 * k, dk + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+          umma_commit(s_full(t));
+          if (last) umma_commit(kq_empty(n & 1));              // every MMA that reads pair n's K / Q has been issued
+        }
+        __syncwarp();
       };
       // scores that involve the 257th key / query row of pair n, written into the tail columns of tile t's region
       // (free from the end of the tile's softmax on; read by the softmax threads before the next S overwrites them)
       auto issue_extras = [&](int t, int n) {
         const uint32_t sb = stage_base(n);
         const uint64_t dq = umma_desc_k_sw128(sb + FR_OFF_Q + t * 16384), dkx = umma_desc_k_sw128(sb + FR_OFF_KX);
+        const uint64_t dk0 = umma_desc_k_sw128(sb + FR_OFF_K), dk1 = umma_desc_k_sw128(sb + FR_OFF_K + 16384);
+        const uint64_t dqx = umma_desc_k_sw128(sb + FR_OFF_QX);
         const uint32_t d = tmem_base + 256u * t;
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16(d + FR_COL_E, dq + 2 * k, dkx + 2 * k, idesc_x, k != 0 ? 1u : 0u);      // rows of tile t . k_256
-        if (t == 0) {
-          const uint64_t dk0 = umma_desc_k_sw128(sb + FR_OFF_K), dk1 = umma_desc_k_sw128(sb + FR_OFF_K + 16384);
-          const uint64_t dqx = umma_desc_k_sw128(sb + FR_OFF_QX);
+          for (int k = 0; k < 4; ++k) umma_f16(d + FR_COL_E, dq + 2 * k, dkx + 2 * k, idesc_x, k != 0 ? 1u : 0u);      // rows of tile t . k_256
+          if (t == 0) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(d + FR_COL_L0, dk0 + 2 * k, dqx + 2 * k, idesc_x, k != 0 ? 1u : 0u);   // keys 0..127 . q_256
+            for (int k = 0; k < 4; ++k) umma_f16(d + FR_COL_L0, dk0 + 2 * k, dqx + 2 * k, idesc_x, k != 0 ? 1u : 0u);   // keys 0..127 . q_256
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(d + FR_COL_L1, dk1 + 2 * k, dqx + 2 * k, idesc_x, k != 0 ? 1u : 0u);   // keys 128..255 . q_256
+            for (int k = 0; k < 4; ++k) umma_f16(d + FR_COL_L1, dk1 + 2 * k, dqx + 2 * k, idesc_x, k != 0 ? 1u : 0u);   // keys 128..255 . q_256
+          }
+          umma_commit(e_full(t));
         }
+        __syncwarp();
       };
       // O_t(n) = P_t V: P from tensor memory (8 columns = 16 keys per k-step), V as MN-major operand (+2048 B per k-step)
-      auto issue_pv = [&](int t, int n) {
+      // O_t(n) = P_t V: P from tensor memory (8 columns = 16 keys per k-step), V as MN-major operand (+2048 B per k-step);
+      // commits o_full(t) and, with `last`, hands the pair's V back to the producer.  Commits are issued by the same
+      // elected lane as the MMAs they track.
+      auto issue_pv = [&](int t, int n, bool last) {
         const uint32_t sb = stage_base(n);
-        const uint64_t dv = umma_desc_mn_sw128(sb + FR_OFF_V);
+        const uint64_t dv = umma_desc_mn_sw128(sb + FR_OFF_V), dvx = umma_desc_mn_sw128(sb + FR_OFF_VX);
         const uint32_t d = tmem_base + 256u * t;
-        const int ksteps = Nk >> 4;
-        for (int k = 0; k < ksteps; ++k) umma_f16_ts(d + FR_COL_O, d + 8u * k, dv + 128ull * k, idesc_pv, k != 0 ? 1u : 0u);
-        if (leftover) umma_f16_ts(d + FR_COL_O, d + FR_COL_PX, umma_desc_mn_sw128(sb + FR_OFF_VX), idesc_pv, 1u);
+        if (elect_one_sync()) {
+          if (ksteps == 16) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) umma_f16_ts(d + FR_COL_O, d + 8u * k, dv + 128ull * k, idesc_pv, k != 0 ? 1u : 0u);
+          } else {
+            for (int k = 0; k < ksteps; ++k) umma_f16_ts(d + FR_COL_O, d + 8u * k, dv + 128ull * k, idesc_pv, k != 0 ? 1u : 0u);
+          }
+          if (leftover) umma_f16_ts(d + FR_COL_O, d + FR_COL_PX, dvx, idesc_pv, 1u);
+          umma_commit(o_full(t));
+          if (last) umma_commit(v_empty(n & 1));               // every MMA that reads pair n's V has been issued
+        }
+        __syncwarp();
       };
-      // prologue: pair 0's extras (or a bare commit, so that o_full completes once per pair index in every mode)
-      mbar_wait(qkv_full(0), 0);
+      // prologue: pair 0's extras, o_full's completion #0 (a bare commit: nothing to drain yet), then S(0)
+      mbar_wait(kq_full(0), 0);
       tcgen05_fence_after();
       for (int t = 0; t < ntiles; ++t) {
         if (leftover) issue_extras(t, 0);
-        umma_commit(o_full(t));
+        if (elect_one_sync()) umma_commit(o_full(t));
+        __syncwarp();
       }
       for (int t = 0; t < ntiles; ++t) {
         mbar_wait(o_read(t), 0);
         tcgen05_fence_after();
-        issue_s(t, 0);
+        issue_s(t, 0, t == ntiles - 1);
       }
       for (int n = 0; n < n_local; ++n) {
+        const bool more = n + 1 < n_local;
         for (int t = 0; t < ntiles; ++t) {
           mbar_wait(p_full(t), n & 1);
+          if (lane == 0) FR_TRACE_M(8 * t + 0);
+          if (t == 0) mbar_wait(v_full(n & 1), (n >> 1) & 1);
           tcgen05_fence_after();
-          issue_pv(t, n);
-          const bool more = n + 1 < n_local;
+          issue_pv(t, n, t == ntiles - 1);
+          if (lane == 0) FR_TRACE_M(8 * t + 1);
           if (more) {
-            mbar_wait(qkv_full((n + 1) & 1), ((n + 1) >> 1) & 1);
+            if (t == 0) { mbar_wait(kq_full((n + 1) & 1), ((n + 1) >> 1) & 1); tcgen05_fence_after(); }
+            if (leftover) issue_extras(t, n + 1);              // behind the P.V in the tensor pipe; its own barrier (e_full)
+            mbar_wait(o_read(t), (n + 1) & 1);                 // tile t's threads have drained O(n) and the extras of n + 1
+            if (lane == 0) FR_TRACE_M(8 * t + 2);
             tcgen05_fence_after();
-            if (leftover) issue_extras(t, n + 1);
-          }
-          umma_commit(o_full(t));
-          if (t == ntiles - 1) umma_commit(qkv_empty(n & 1));      // every MMA that reads pair n's stage has been issued
-          if (more) {
-            mbar_wait(o_read(t), (n + 1) & 1);                     // tile t's threads have drained O(n) and the extras of n + 1
-            tcgen05_fence_after();
-            issue_s(t, n + 1);
+            issue_s(t, n + 1, t == ntiles - 1);
+            if (lane == 0) FR_TRACE_M(8 * t + 3);
           }
         }
       }
@@ -202,11 +254,12 @@ attn_fullrow_hd64_kernel(const __grid_constant__ CUtensorMap tm256, const __grid
         const int b = g / p.heads, h = g % p.heads;
         const uint8_t* sb = smem + (n & 1) * FR_STAGE_BYTES;
         float* pl = p_left + (n & 1) * FR_PLEFT_STRIDE;
-        mbar_wait(qkv_full(n & 1), (n >> 1) & 1);
+        mbar_wait(kq_full(n & 1), (n >> 1) & 1);
         // q_256 . k_256 (row 0 of a 128B-swizzled tile is stored unswizzled): two dims per lane
         const float2 qv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(sb + FR_OFF_QX + 4 * lane));
         const float2 kv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(sb + FR_OFF_KX + 4 * lane));
         const float s_self = warp_sum(fmaf(qv.x, kv.x, qv.y * kv.y));
+        if (lane == 0) mbar_arrive(kq_empty(n & 1));        // this warp is done with the pair's K / Q group
         mbar_wait(left_s, n & 1);                            // tile A's threads have stored the 256 scores of this row
         float sv[8];
         float mx = s_self;
@@ -226,17 +279,18 @@ attn_fullrow_hd64_kernel(const __grid_constant__ CUtensorMap tm256, const __grid
         __syncwarp();
         if (lane == 0) mbar_arrive(left_p);
         mbar_wait(left_o, n & 1);                            // the eight softmax warps have summed their 32-key slices of P.V
-        const float* pt = part + (n & 1) * 8 * 64;
+        const float* pt = part;
         float o0 = 0.f, o1 = 0.f;
 #pragma unroll
         for (int w = 0; w < 8; ++w) { const float2 v = *reinterpret_cast<const float2*>(pt + w * 64 + 2 * lane); o0 += v.x; o1 += v.y; }
+        mbar_wait(v_full(n & 1), (n >> 1) & 1);
         const float2 vx = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(sb + FR_OFF_VX + 4 * lane));
         const float inv = 1.0f / sum;
         o0 = fmaf(e_self, vx.x, o0) * inv;
         o1 = fmaf(e_self, vx.y, o1) * inv;
         *reinterpret_cast<uint32_t*>(p.out + (static_cast<long long>(b) * T + 256) * C + h * 64 + 2 * lane) = pack_bf16x2(o0, o1);
         __syncwarp();
-        if (lane == 0) mbar_arrive(qkv_empty(n & 1));        // all CUDA-core readers of this stage are done
+        if (lane == 0) mbar_arrive(v_empty(n & 1));          // all CUDA-core readers of this pair's V are done
       }
     }
   } else if ((warp >> 2) < ntiles) {
@@ -252,10 +306,13 @@ attn_fullrow_hd64_kernel(const __grid_constant__ CUtensorMap tm256, const __grid
     for (int n = 0; n_local > 0 && n <= n_local; ++n) {
       const int g = static_cast<int>(blockIdx.x) + (n - 1) * static_cast<int>(gridDim.x);     // pair whose O is drained now
       mbar_wait(o_full(t), n & 1);
+      FR_TRACE(t, 0);
       tcgen05_fence_after();
       float s_x = -INFINITY;
       if (leftover && n < n_local) {
         // scores against the 257th key (this row) and of the 257th row (this lane's key), parked in the region's tail
+        mbar_wait(e_full(t), n & 1);
+        tcgen05_fence_after();
         s_x = __uint_as_float(tmem_ld_32x32b_x1(treg + FR_COL_E));
         if (t == 0) {
           const float l0 = __uint_as_float(tmem_ld_32x32b_x1(treg + FR_COL_L0));
@@ -267,26 +324,20 @@ attn_fullrow_hd64_kernel(const __grid_constant__ CUtensorMap tm256, const __grid
           tmem_ld_wait();
         }
       }
+      uint4 ov[8];
       if (n > 0) {
-        // O(n-1) / l -> bf16 -> global
-        const int b = g / p.heads, h = g % p.heads;
-        const int grow = t * 128 + row;
-        bf16* dst = p.out + (static_cast<long long>(b) * T + grow) * C + h * 64;
+        // O(n-1) / l -> bf16, held in registers so that the region can be handed back before anything is stored
 #pragma unroll
         for (int c0 = 0; c0 < 64; c0 += 32) {
           uint32_t o[32];
           tmem_ld_32x32b_x32(treg + FR_COL_O + c0, o);
           tmem_ld_wait();
-          if (grow < T) {
 #pragma unroll
-            for (int v4 = 0; v4 < 4; ++v4) {
-              uint4 u;
-              u.x = pack_bf16x2(__uint_as_float(o[8 * v4 + 0]) * inv_l, __uint_as_float(o[8 * v4 + 1]) * inv_l);
-              u.y = pack_bf16x2(__uint_as_float(o[8 * v4 + 2]) * inv_l, __uint_as_float(o[8 * v4 + 3]) * inv_l);
-              u.z = pack_bf16x2(__uint_as_float(o[8 * v4 + 4]) * inv_l, __uint_as_float(o[8 * v4 + 5]) * inv_l);
-              u.w = pack_bf16x2(__uint_as_float(o[8 * v4 + 6]) * inv_l, __uint_as_float(o[8 * v4 + 7]) * inv_l);
-              *reinterpret_cast<uint4*>(dst + c0 + 8 * v4) = u;
-            }
+          for (int v4 = 0; v4 < 4; ++v4) {
+            ov[c0 / 8 + v4].x = pack_bf16x2(__uint_as_float(o[8 * v4 + 0]) * inv_l, __uint_as_float(o[8 * v4 + 1]) * inv_l);
+            ov[c0 / 8 + v4].y = pack_bf16x2(__uint_as_float(o[8 * v4 + 2]) * inv_l, __uint_as_float(o[8 * v4 + 3]) * inv_l);
+            ov[c0 / 8 + v4].z = pack_bf16x2(__uint_as_float(o[8 * v4 + 4]) * inv_l, __uint_as_float(o[8 * v4 + 5]) * inv_l);
+            ov[c0 / 8 + v4].w = pack_bf16x2(__uint_as_float(o[8 * v4 + 6]) * inv_l, __uint_as_float(o[8 * v4 + 7]) * inv_l);
           }
         }
       }
@@ -296,14 +347,42 @@ attn_fullrow_hd64_kernel(const __grid_constant__ CUtensorMap tm256, const __grid
         mbar_arrive(o_read(t));                              // the region may take the next S
         if (leftover && t == 0 && n < n_local) mbar_arrive(left_s);
       }
+      FR_TRACE(t, 1);
+      if (n > 0) {
+        // rows -> global through this warp's 2 KiB of staging, 16 rows per round: a thread owns a row in tensor memory, but a
+        // coalesced store wants 8 lanes on one 128-byte row; both shared-memory sides are conflict-free (XOR swizzle)
+        const int b = g / p.heads, h = g % p.heads;
+        uint8_t* stg = smem + FR_OFF_STG + warp * 2048;
+#pragma unroll
+        for (int rnd = 0; rnd < 2; ++rnd) {
+          if ((lane >> 4) == rnd) {
+            const int lr = lane & 15;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(stg + lr * 128 + ((c ^ (lr & 7)) << 4)) = ov[c];
+          }
+          __syncwarp();
+          if (!(p.dbg & 8)) {
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int lr = it * 4 + (lane >> 3), c = lane & 7;
+              const uint4 v = *reinterpret_cast<const uint4*>(stg + lr * 128 + ((c ^ (lr & 7)) << 4));
+              const int grow = t * 128 + q * 32 + rnd * 16 + lr;
+              if (grow < T) *reinterpret_cast<uint4*>(p.out + (static_cast<long long>(b) * T + grow) * C + h * 64 + c * 8) = v;
+            }
+          }
+          __syncwarp();
+        }
+      }
       if (n == n_local) break;
 
+      FR_TRACE(t, 2);
       mbar_wait(s_full(t), n & 1);
+      FR_TRACE(t, 3);
       tcgen05_fence_after();
       // pass 1: row maximum over the keys
       float mx0 = s_x, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < nchunks; ++c) {
+      for (int c = 0; c < ((p.dbg & 1) ? 0 : nchunks); ++c) {
         uint32_t r[64];
         tmem_ld_32x32b_x32(treg + 64 * c, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
         tmem_ld_32x32b_x32(treg + 64 * c + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
@@ -318,7 +397,10 @@ attn_fullrow_hd64_kernel(const __grid_constant__ CUtensorMap tm256, const __grid
           mx2 = fmaxf(mx2, __uint_as_float(r[i + 2])); mx3 = fmaxf(mx3, __uint_as_float(r[i + 3]));
         }
       }
-      const float m = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sl2;
+      FR_TRACE(t, 4);
+      const float m = (p.dbg & 1) ? 8.0f : fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sl2;
+      const bool no_exp = (p.dbg & 2) != 0;
+      const bool packed_exp = (p.dbg & 16) != 0;
       // pass 2: p = exp2(s * scale - m); P (bf16 pairs) goes back over the S columns already consumed
       float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
 #pragma unroll 1
@@ -331,17 +413,32 @@ attn_fullrow_hd64_kernel(const __grid_constant__ CUtensorMap tm256, const __grid
 #pragma unroll
           for (int i = 0; i < 64; ++i) if (64 * c + i >= nkeys) r[i] = 0xff800000u;
         }
+        if (packed_exp) {
+          // two exponentials per MUFU op: arguments rounded to bf16 pairs, ex2.approx.ftz.bf16x2 returns the P pair itself
 #pragma unroll
-        for (int i = 0; i < 64; i += 4) {
-          const float p0 = fr_exp2(fmaf(__uint_as_float(r[i]), sl2, -m));
-          const float p1 = fr_exp2(fmaf(__uint_as_float(r[i + 1]), sl2, -m));
-          const float p2 = fr_exp2(fmaf(__uint_as_float(r[i + 2]), sl2, -m));
-          const float p3 = fr_exp2(fmaf(__uint_as_float(r[i + 3]), sl2, -m));
-          ps0 += p0; ps1 += p1; ps2 += p2; ps3 += p3;
-          r[i / 2] = pack_bf16x2(p0, p1);               // in place: slots <= i/2+1 were consumed already
-          r[i / 2 + 1] = pack_bf16x2(p2, p3);
+          for (int i = 0; i < 64; i += 4) {
+            const uint32_t xa = pack_bf16x2(fmaf(__uint_as_float(r[i]), sl2, -m), fmaf(__uint_as_float(r[i + 1]), sl2, -m));
+            const uint32_t xb = pack_bf16x2(fmaf(__uint_as_float(r[i + 2]), sl2, -m), fmaf(__uint_as_float(r[i + 3]), sl2, -m));
+            uint32_t pa, pb;
+            asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(pa) : "r"(xa));
+            asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(pb) : "r"(xb));
+            ps0 += __uint_as_float(pa << 16); ps1 += __uint_as_float(pa & 0xffff0000u);
+            ps2 += __uint_as_float(pb << 16); ps3 += __uint_as_float(pb & 0xffff0000u);
+            r[i / 2] = pa;
+            r[i / 2 + 1] = pb;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 64; i += 4) {
+            float p0 = fmaf(__uint_as_float(r[i]), sl2, -m), p1 = fmaf(__uint_as_float(r[i + 1]), sl2, -m);
+            float p2 = fmaf(__uint_as_float(r[i + 2]), sl2, -m), p3 = fmaf(__uint_as_float(r[i + 3]), sl2, -m);
+            if (!no_exp) { p0 = fr_exp2(p0); p1 = fr_exp2(p1); p2 = fr_exp2(p2); p3 = fr_exp2(p3); }
+            ps0 += p0; ps1 += p1; ps2 += p2; ps3 += p3;
+            r[i / 2] = pack_bf16x2(p0, p1);               // in place: slots <= i/2+1 were consumed already
+            r[i / 2 + 1] = pack_bf16x2(p2, p3);
+          }
         }
-        tmem_st_32x32b_x32(treg + 32 * c, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+        if (!(p.dbg & 4)) tmem_st_32x32b_x32(treg + 32 * c, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
       }
       float l = (ps0 + ps1) + (ps2 + ps3);
       if (leftover) {
@@ -355,9 +452,11 @@ attn_fullrow_hd64_kernel(const __grid_constant__ CUtensorMap tm256, const __grid
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full(t));
+      FR_TRACE(t, 5);
 
       if (leftover) {
         // this warp's 32-key slice of the 257th row's P.V on the CUDA cores: lane <-> dims (2 lane, 2 lane + 1)
+        mbar_wait(v_full(n & 1), (n >> 1) & 1);
         mbar_wait(left_p, n & 1);
         const float* pl = p_left + (n & 1) * FR_PLEFT_STRIDE + 32 * warp;
         const uint8_t* vt = smem + (n & 1) * FR_STAGE_BYTES + FR_OFF_V;
@@ -370,9 +469,10 @@ attn_fullrow_hd64_kernel(const __grid_constant__ CUtensorMap tm256, const __grid
           a0 = fmaf(pj, v.x, a0);
           a1 = fmaf(pj, v.y, a1);
         }
-        *reinterpret_cast<float2*>(part + (n & 1) * 8 * 64 + warp * 64 + 2 * lane) = make_float2(a0, a1);
+        *reinterpret_cast<float2*>(part + warp * 64 + 2 * lane) = make_float2(a0, a1);
         __syncwarp();
         if (lane == 0) mbar_arrive(left_o);
+        FR_TRACE(t, 6);
       }
     }
   }
@@ -400,7 +500,10 @@ EncodeTiledFn fr_encode_fn() {
 
 }  // namespace
 
-bool attention_fullrow_supported(int T) { return g_attn_fullrow != 0 && T >= 1 && T <= 257; }
+bool attention_fullrow_supported(int T) {
+  if (g_attn_fullrow == 0 || T < 1 || T > 257) return false;
+  return g_attn_fullrow == 2 || T >= 225;
+}
 
 // qkv bf16 [B*T, 3C] -> out bf16 [B*T, C]; heads of 64; softmax(q k^T * scale) v per image; T <= 257.
 int launch_attention_fullrow(const void* qkv, void* out, int B, int T, int C, int heads, float scale, cudaStream_t stream) {
@@ -421,6 +524,7 @@ int launch_attention_fullrow(const void* qkv, void* out, int B, int T, int C, in
   FrParams p;
   p.out = static_cast<bf16*>(out); p.T = T; p.heads = heads; p.C = C; p.n_pairs = B * heads;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.dbg = g_attn_fullrow_dbg;
   const int grid = p.n_pairs < num_sms() ? p.n_pairs : num_sms();
   SETOK_CUDA_OK(launch_pdl(attn_fullrow_hd64_kernel, dim3(grid), dim3(FR_THREADS), FR_SMEM_BYTES, stream, tm256, tm16, p));
   SETOK_LAUNCH_CHECK();
@@ -430,3 +534,7 @@ int launch_attention_fullrow(const void* qkv, void* out, int B, int T, int C, in
 }  // namespace setok
 
 extern "C" void setok_debug_set_attention_fullrow(int on) { setok::g_attn_fullrow = on; }
+extern "C" void setok_debug_set_attention_fullrow_dbg(int flags) { setok::g_attn_fullrow_dbg = flags; }
+#ifdef SETOK_ATTN_TRACE
+extern "C" void setok_debug_set_fullrow_trace(void* buf) { cudaMemcpyToSymbol(setok::g_fr_trace, &buf, sizeof buf); }
+#endif

@@ -159,7 +159,19 @@ def test_attention_vit_hd64(T, B, heads):
     qkv = torch.randn(B * T, 3 * C, generator=g).to(DEV, torch.bfloat16)
     so = torch.arange(0, B * T + 1, T, dtype=torch.int32)
     out = ops.attention(qkv, heads, 0.125, uniform_T=T)
-    _close(out, _attn_ref(qkv, heads, 0.125, so), 6e-3, "vit attention")
+    ref = _attn_ref(qkv, heads, 0.125, so)
+    _close(out, ref, 6e-3, "vit attention")
+    # both kernels on every shape they accept (the dispatcher picks the whole-row kernel only for 225 <= T <= 257)
+    import ctypes
+    from setok_b200 import _lib
+    lib = _lib.load()
+    lib.setok_debug_set_attention_fullrow.argtypes = [ctypes.c_int]
+    try:
+        for mode in (2, 0):
+            lib.setok_debug_set_attention_fullrow(mode)
+            _close(ops.attention(qkv, heads, 0.125, uniform_T=T), ref, 6e-3, f"vit attention (fullrow mode {mode})")
+    finally:
+        lib.setok_debug_set_attention_fullrow(1)
 
 
 @pytest.mark.parametrize("Bt,M,N,K,mn", [(3, 256, 256, 512, False), (5, 196, 196, 384, False), (4, 256, 512, 256, True), (3, 196, 384, 196, True), (2, 576, 512, 576, True),

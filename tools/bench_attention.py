@@ -32,14 +32,26 @@ def main():
         C = 64 * H
         qkv = torch.randn(B * T, 3 * C, device=dev).to(torch.bfloat16)
         outs = {}
-        for mode, name in ((1, "fullrow"), (0, "chunked")):
+        for mode, name in ((2, "fullrow"), (0, "chunked")):
             lib.setok_debug_set_attention_fullrow(mode)
             ms = timeit(lambda: ops.attention(qkv, H, 0.125, uniform_T=T))
             outs[name] = ops.attention(qkv, H, 0.125, uniform_T=T).float()
             print(f"attention T={T} B={B} heads={H} {name:8s}: {ms * 1e3:8.1f} us  {4.0 * T * T * C * B / ms / 1e9:8.1f} TFLOP/s")
-        lib.setok_debug_set_attention_fullrow(1)
         d = (outs["fullrow"] - outs["chunked"]).abs().max().item()
         print(f"   max |fullrow - chunked| = {d:.3e}")
+        if T == 257 and B == 256:
+            lib.setok_debug_set_attention_fullrow_dbg.argtypes = [ctypes.c_int]
+            lib.setok_debug_set_attention_fullrow(2)
+            for flags, what in ((1, "no pass 1"), (2, "no exp2"), (3, "no pass 1, no exp2"), (4, "no P store"), (8, "no O store"), (15, "all off"), (16, "packed bf16x2 exp2")):
+                lib.setok_debug_set_attention_fullrow_dbg(flags)
+                ms = timeit(lambda: ops.attention(qkv, H, 0.125, uniform_T=T))
+                extra = ""
+                if flags == 16:
+                    d16 = (ops.attention(qkv, H, 0.125, uniform_T=T).float() - outs["fullrow"]).abs().max().item()
+                    extra = f"   max |packed - f32 exp| = {d16:.3e}"
+                print(f"   fullrow with {what:20s}: {ms * 1e3:8.1f} us{extra}")
+            lib.setok_debug_set_attention_fullrow_dbg(0)
+        lib.setok_debug_set_attention_fullrow(1)
 
 
 if __name__ == "__main__":
