@@ -8,6 +8,7 @@ from .ragged import RaggedTokens  # noqa: F401
 from .tokenizer import CLIPVisionTower, SetokTokenizer  # noqa: F401
 from .detokenizer import SetokDeTokenizer  # noqa: F401
 from .splice import prepare_inputs_labels_for_multimodal  # noqa: F401
+from .preprocess import preprocess_images, process_images  # noqa: F401
 
 __all__ = ["SetokTokenizer", "SetokDeTokenizer", "CLIPVisionTower", "RaggedTokens", "build_vision_tower", "build_vision_projector",
-           "encode_images", "prepare_inputs_labels_for_multimodal", "SetokError"]
+           "encode_images", "prepare_inputs_labels_for_multimodal", "process_images", "preprocess_images", "SetokError"]

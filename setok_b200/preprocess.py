@@ -141,10 +141,13 @@ def process_images(images: Sequence, image_processor, model_cfg=None, device: Op
     aspect = getattr(model_cfg, "image_aspect_ratio", None) if model_cfg is not None else None
     if aspect == "anyres":
         raise SetokError("image_aspect_ratio='anyres' is not supported by the device preprocessing path")
-    crop = getattr(image_processor, "crop_size", None) or {}
-    size = getattr(image_processor, "size", None) or {}
-    S = int(crop.get("height", 0) or size.get("shortest_edge", 0) or 0)
-    if S <= 0 or (size.get("shortest_edge", S) != S) or crop.get("width", S) != S:
+    def field(obj, key):                                 # dict (transformers 4.x) or SizeDict (5.x)
+        if obj is None:
+            return None
+        return obj.get(key) if isinstance(obj, dict) else getattr(obj, key, None)
+    crop, size = getattr(image_processor, "crop_size", None), getattr(image_processor, "size", None)
+    S = int(field(crop, "height") or field(size, "shortest_edge") or 0)
+    if S <= 0 or (field(size, "shortest_edge") or S) != S or (field(crop, "width") or S) != S:
         raise SetokError("device preprocessing needs a square crop equal to the processor's shortest_edge")
     mean = tuple(getattr(image_processor, "image_mean", None) or (0.48145466, 0.4578275, 0.40821073))
     return preprocess_images(images, S, pad=(aspect == "pad"), image_mean=mean, device=device)
