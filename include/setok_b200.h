@@ -329,6 +329,43 @@ int setok_preprocess_u8(const setok_resize_desc* descs, int B, int max_rows, con
                         const uint8_t* background, uint8_t* out, void* workspace, size_t workspace_bytes,
                         size_t workspace_needed, setok_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * primitives of the head's training path -- what torch.autograd does implicitly for the reference when
+ * gradients flow through group_encoding / inter_encoder / out (src/model/setok/tokenizer.py:123-155, 179-180, Block /
+ * Attention / Mlp module.py:29-100) and mm_projector (multimodal_projector/builder.py:33-64).  The contractions of the
+ * backward pass run on setok_gemm_bf16_batched (dgrad: dX = dY W with W [N, K] as the MN-major operand; wgrad:
+ * dW = dY^T X with X [M, K] as the MN-major operand and dY^T from setok_transpose_to_bf16); these are the row kernels in
+ * between.  setok_b200/training.py composes them into torch.autograd Functions.
+ */
+/* out[b][c][r] = bf16(in[b][r][c]); in f32|bf16 with leading dimension ld_in, batch strides in elements */
+int setok_transpose_to_bf16(const void* in, int in_dtype, int64_t ld_in, int64_t in_batch_stride, void* out, int64_t ld_out,
+                            int64_t out_batch_stride, int rows, int cols, int batch, setok_stream_t stream);
+/* out[c] += sum_r in[r][c]  (bias gradients; the caller zeroes `out`) */
+int setok_colsum_add(const void* in, int in_dtype, int64_t ld, int rows, int cols, float* out, setok_stream_t stream);
+/* LayerNorm backward from the saved input x (f32): dx (f32) written, dgamma / dbeta (f32 [C]) accumulated */
+int setok_layernorm_bwd(const float* x, const void* dy, int dy_dtype, const float* gamma, float eps, int rows, int C,
+                        float* dx, float* dgamma, float* dbeta, setok_stream_t stream);
+/* GELU(erf): act = gelu(pre) as bf16; dpre = dy * gelu'(pre) */
+int setok_gelu_fwd(const void* pre, int pre_dtype, void* act_bf16, int64_t n, setok_stream_t stream);
+int setok_gelu_bwd(const void* pre, int pre_dtype, const void* dy, int dy_dtype, float* dpre, int64_t n, setok_stream_t stream);
+/* Dense masked attention of the cluster encoders, middle step and its backward: rows are N-token images sorted by segment;
+ * row r may attend columns [seg_off[s] - image start, seg_off[s+1] - image start), s = row_seg[r].
+ *   P = softmax(scale * S) inside the segment, 0 outside (bf16);  dS = scale * P * (dP - sum_k P dP) (bf16) */
+int setok_masked_softmax(const float* S, int64_t ldS, const int32_t* seg_off, const int32_t* row_seg, int rows, int N, float scale,
+                         void* P_bf16, int64_t ldP, setok_stream_t stream);
+int setok_masked_softmax_bwd(const void* P_bf16, int64_t ldP, const float* dP, int64_t lddP, const int32_t* seg_off,
+                             const int32_t* row_seg, int rows, int N, float scale, void* dS_bf16, int64_t lddS,
+                             setok_stream_t stream);
+/* tokenizer.py:141-151 bookkeeping: stable sort of every image's tokens by cluster label (perm, row_seg, seg_off as in
+ * setok_head_forward), the per-cluster mean and its backward */
+int setok_sort_by_cluster(const int64_t* idx_cluster, const int32_t* num_clusters, const int32_t* offsets, int B, int N,
+                          int32_t* perm, int32_t* row_seg, int32_t* seg_off, setok_stream_t stream);
+int setok_segment_mean(const float* x, const int32_t* seg_off, int n_segments, int C, float* out, setok_stream_t stream);
+int setok_segment_mean_bwd(const float* dg, const int32_t* seg_off, const int32_t* row_seg, int rows, int C, float* dx,
+                           setok_stream_t stream);
+/* out[r] = index[r] >= 0 ? in[index[r]] : 0   (f32 rows; pads / unpads ragged batches, applies permutations) */
+int setok_gather_rows_f32(const float* in, const int32_t* index, int rows_out, int C, float* out, setok_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -116,6 +116,17 @@ SIGNATURES = {
     "setok_splice": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "setok_preprocess_u8": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_void_p]),
+    "setok_transpose_to_bf16": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p]),
+    "setok_colsum_add": (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p]),
+    "setok_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "setok_gelu_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p]),
+    "setok_gelu_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int64, c_void_p]),
+    "setok_masked_softmax": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_int64, c_void_p]),
+    "setok_masked_softmax_bwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_int64, c_void_p]),
+    "setok_sort_by_cluster": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "setok_segment_mean": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "setok_segment_mean_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "setok_gather_rows_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "setok_project_workspace_bytes": (c_size_t, [C.POINTER(Projector), c_int]),
     "setok_project": (c_int, [C.POINTER(Projector), c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
 }

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsetok_b200.so")
-SOURCES = ["core.cu", "gemm_tcgen05.cu", "attention.cu", "attention_tcgen05.cu", "attention_fullrow.cu", "rowops.cu", "dpc.cu", "dpc_fused.cu", "splice.cu", "preprocess.cu", "api.cu"]
+SOURCES = ["core.cu", "gemm_tcgen05.cu", "attention.cu", "attention_tcgen05.cu", "attention_fullrow.cu", "rowops.cu", "dpc.cu", "dpc_fused.cu", "splice.cu", "preprocess.cu", "train.cu", "api.cu"]
 HEADERS = ["common.cuh", "rowops.cuh", os.path.join("..", "..", "include", "setok_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]

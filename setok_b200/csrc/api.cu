@@ -138,6 +138,7 @@ namespace {
 int vit_forward_impl(const setok_vit* v, const void* images, int image_dtype, int B, int n_layers_run, int keep_cls, void* features,
                      int feature_dtype, const float* pos_add, void* workspace, size_t workspace_bytes, cudaStream_t stream,
                      const setok_u8_norm* u8norm = nullptr) {
+  SETOK_NVTX("setok a1+a2(+a3) vision tower");
   SETOK_TRY(check_vit(v));
   SETOK_REQUIRE(images && features && B > 0, SETOK_ERR_BAD_ARG, "vit_forward: null images/features or B <= 0");
   SETOK_REQUIRE(n_layers_run >= 0 && n_layers_run <= v->layers, SETOK_ERR_BAD_ARG, "vit_forward: n_layers_run %d outside [0, %d]", n_layers_run, v->layers);
@@ -212,6 +213,7 @@ extern "C" size_t setok_head_workspace_bytes(const setok_head* head, int B, int 
 extern "C" int setok_head_forward(const setok_head* hd, const float* x_pos, const int64_t* idx_cluster, const int32_t* num_clusters,
                                   const int32_t* offsets, int B, int N, void* tokens, int token_dtype, float* group_features,
                                   void* workspace, size_t workspace_bytes, setok_stream_t stream_) {
+  SETOK_NVTX("setok a5+a6 cluster encoders");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SETOK_REQUIRE(hd && x_pos && idx_cluster && num_clusters && offsets && tokens, SETOK_ERR_BAD_ARG, "head_forward: null pointer");
   SETOK_REQUIRE(B > 0 && N > 0, SETOK_ERR_BAD_ARG, "head_forward: B=%d N=%d", B, N);
@@ -259,6 +261,7 @@ extern "C" size_t setok_project_workspace_bytes(const setok_projector* p, int ro
 
 extern "C" int setok_project(const setok_projector* p, const void* tokens, int token_dtype, int rows, const int32_t* m_dev,
                              void* out, int out_dtype, void* workspace, size_t workspace_bytes, setok_stream_t stream_) {
+  SETOK_NVTX("setok a8 mm_projector");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SETOK_REQUIRE(p && tokens && out && rows > 0, SETOK_ERR_BAD_ARG, "project: null pointer or rows <= 0");
   SETOK_REQUIRE(p->n_linear >= 1 && p->w && p->b && p->dims, SETOK_ERR_BAD_ARG, "project: bad projector description");
@@ -340,6 +343,7 @@ extern "C" size_t setok_detok_workspace_bytes(const setok_detok* d, int B, int r
 
 extern "C" int setok_detok_forward(const setok_detok* d, const void* tokens, int token_dtype, const int32_t* offsets, int B, int cap,
                                    void* out, int out_dtype, void* workspace, size_t workspace_bytes, setok_stream_t stream_) {
+  SETOK_NVTX("setok a10 detokenizer");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SETOK_REQUIRE(d && tokens && offsets && out, SETOK_ERR_BAD_ARG, "detok_forward: null pointer");
   SETOK_REQUIRE(B > 0 && cap > 0 && d->grid > 0, SETOK_ERR_BAD_ARG, "detok_forward: B=%d rows_capacity=%d grid=%d", B, cap, d->grid);

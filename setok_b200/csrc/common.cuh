@@ -11,6 +11,8 @@
 #include <cstdio>
 #include <cstring>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/setok_b200.h"
 
 namespace setok {
@@ -59,6 +61,13 @@ inline int fail(int code, const char* fmt, ...) {
     int _s = (expr);             \
     if (_s != SETOK_OK) return _s; \
   } while (0)
+
+// NVTX range around each SURVEY.md 8 row's entry point (a no-op unless a profiler is attached): SETOK_NVTX("a1+a2 ...").
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+#define SETOK_NVTX(name) ::setok::NvtxRange _setok_nvtx_range(name)
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

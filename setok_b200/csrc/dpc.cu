@@ -377,6 +377,7 @@ int dpc_cluster_impl(const void* feats, int feat_dtype, const float* pos_table, 
                      int min_cluster_num, float* x_pos, int64_t* idx_cluster, float* score, int64_t* index_down,
                      int32_t* num_clusters, int32_t* offsets, void* workspace, size_t workspace_bytes,
                      cudaStream_t stream) {
+  SETOK_NVTX("setok a3+a4 position embedding + DPC-kNN clustering");
   const int N = h * w;
   SETOK_REQUIRE(feats && noise && (x_pos || embedded) && idx_cluster && score && index_down && num_clusters && offsets, SETOK_ERR_BAD_ARG, "dpc_cluster: null pointer");
   SETOK_REQUIRE(B > 0 && h > 0 && w > 0 && C > 0, SETOK_ERR_BAD_ARG, "dpc_cluster: non-positive shape");

@@ -94,6 +94,7 @@ using namespace setok;
 extern "C" int setok_preprocess_u8(const setok_resize_desc* descs_dev, int B, int max_rows, const int32_t* tables_dev, int S,
                                    const uint8_t* background, uint8_t* out, void* workspace, size_t workspace_bytes, size_t workspace_needed,
                                    setok_stream_t stream_) {
+  SETOK_NVTX("setok f3 image preprocessing");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SETOK_REQUIRE(descs_dev && tables_dev && out && workspace && background, SETOK_ERR_BAD_ARG, "preprocess_u8: null pointer");
   SETOK_REQUIRE(B > 0 && S > 0 && max_rows > 0, SETOK_ERR_BAD_ARG, "preprocess_u8: B=%d S=%d max_rows=%d", B, S, max_rows);

@@ -171,6 +171,7 @@ void splice_carve(int B, int out_cap, Arena& a, SpliceWs* w) {
 extern "C" int setok_splice_plan(const int64_t* input_ids, const uint8_t* attention_mask, int B, int L, const int32_t* image_offsets, int n_images,
                                  int max_length, int out_cap_limit, int32_t* lens, int32_t* max_len, void* workspace, size_t workspace_bytes,
                                  setok_stream_t stream_) {
+  SETOK_NVTX("setok a9 splice plan");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SETOK_REQUIRE(input_ids && image_offsets && lens && max_len, SETOK_ERR_BAD_ARG, "splice_plan: null pointer");
   SETOK_REQUIRE(B > 0 && L > 0 && n_images >= 0 && out_cap_limit > 0, SETOK_ERR_BAD_ARG, "splice_plan: bad shape B=%d L=%d", B, L);
@@ -190,6 +191,7 @@ extern "C" int setok_splice_fill(const int64_t* input_ids, const uint8_t* attent
                                  int dtype, int V, int H, const void* image_rows, const int32_t* image_offsets, int n_images, int pad_left,
                                  int out_cap, const int32_t* lens, const int32_t* max_len, void* embeds, int64_t* labels_out, uint8_t* mask_out,
                                  int64_t* pos_out, void* workspace, size_t workspace_bytes, setok_stream_t stream_) {
+  SETOK_NVTX("setok a9 splice fill");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SETOK_REQUIRE(input_ids && embed && image_rows && image_offsets && embeds && labels_out && mask_out && pos_out && lens && max_len,
                 SETOK_ERR_BAD_ARG, "splice_fill: null pointer");

@@ -80,8 +80,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
 
 
 def gemm_batched(a: torch.Tensor, w: torch.Tensor, *, w_mn_major: bool = False, out_dtype=torch.bfloat16, bias: Optional[torch.Tensor] = None,
-                 act: int = ACT_NONE) -> torch.Tensor:
-    """a (B, M, K) bf16 (row stride may exceed K); w (B, N, K) or, with w_mn_major, (B, K, N).  Returns (B, M, N)."""
+                 act: int = ACT_NONE, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """a (B, M, K) bf16 (row stride may exceed K); w (B, N, K) or, with w_mn_major, (B, K, N).  Returns (B, M, N); `out` may
+    be a strided view (unit inner stride), e.g. one head's columns of a packed buffer."""
     if a.dtype != torch.bfloat16 or w.dtype != torch.bfloat16 or a.dim() != 3 or w.dim() != 3:
         raise SetokError("gemm_batched needs 3-D bfloat16 operands")
     if not a.is_cuda or a.stride(2) != 1 or w.stride(2) != 1:
@@ -89,7 +90,10 @@ def gemm_batched(a: torch.Tensor, w: torch.Tensor, *, w_mn_major: bool = False, 
     dev = a.device
     Bt, M, K = a.shape
     N = w.shape[2] if w_mn_major else w.shape[1]
-    out = torch.empty(Bt, M, N, dtype=out_dtype, device=dev)
+    if out is None:
+        out = torch.empty(Bt, M, N, dtype=out_dtype, device=dev)
+    elif tuple(out.shape) != (Bt, M, N) or out.stride(2) != 1 or not out.is_cuda:
+        raise SetokError(f"gemm_batched: out must be a CUDA ({Bt}, {M}, {N}) tensor with a unit inner stride")
     with torch.cuda.device(dev):
         st = _lib.load().setok_gemm_bf16_batched(a.data_ptr(), a.stride(1), a.stride(0), w.data_ptr(), w.stride(1), w.stride(0), int(w_mn_major),
                                                  out.data_ptr(), out.stride(1), out.stride(0), _dt(out), _p(bias), act, Bt, M, N, K, _stream(dev))

@@ -541,9 +541,42 @@ class SetokTokenizer(PackedParams, nn.Module):
             return rt, idx, score.unsqueeze(1), RaggedTokens(gf, offs)
         return rt, idx, score.unsqueeze(1)
 
-    @torch.no_grad()
     def forward(self, x, k=None, threshold=None, token_mask=None, noise=None, interpolate_pos_encoding: bool = False,
                 token_dtype: Optional[torch.dtype] = None):
+        """Inference (`eval()` or grad disabled): the fused path below.  `train()` with gradients enabled and a trainable
+        head: `forward_train` (autograd through group_encoding / inter_encoder / out, as in the reference where only the
+        tower and the clustering are under no_grad: clip_encoder.py:50, tokenizer.py:79)."""
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.out.parameters()) and torch.is_tensor(x):
+            return self.forward_train(x, k=k, threshold=threshold, token_mask=token_mask, noise=noise, interpolate_pos_encoding=interpolate_pos_encoding)
+        return self._forward_inference(x, k=k, threshold=threshold, token_mask=token_mask, noise=noise,
+                                       interpolate_pos_encoding=interpolate_pos_encoding, token_dtype=token_dtype)
+
+    def forward_train(self, x, k=None, threshold=None, token_mask=None, noise=None, interpolate_pos_encoding: bool = False):
+        """Images (B, 3, H, W) -> the reference's 3-tuple with float32 tokens that carry a graph back to the head's parameters
+        (setok_b200/training.py).  Tower and clustering run without gradients, exactly where the reference disables them."""
+        from . import training
+        tower = self.image_feature_encoder
+        with torch.no_grad():
+            if tower.select_feature != "patch":
+                raise SetokError("forward_train needs mm_vision_select_feature='patch'")
+            x_pos = tower(x, interpolate_pos_encoding, pos_embedding=self.position_embedding)
+            B, N, _ = x_pos.shape
+            h = w = int(math.sqrt(N))
+            _threshold = threshold if threshold else self.threshold
+            _k = k if k else self.min_cluster_num
+            dev = self.device
+            noise = torch.rand(B, N, device=dev, dtype=torch.float32) if noise is None else noise.to(device=dev, dtype=torch.float32).reshape(B, N).contiguous()
+            if token_mask is not None:
+                token_mask = token_mask.to(dev).reshape(B, N)
+            _, idx, score, down, numc, offs = ops.dpc_cluster(x_pos, noise, (h, w), int(_k), float(_threshold), int(self.min_cluster_num),
+                                                              token_mask=token_mask, embedded=True)
+        rt = training.head_forward_train(self, x_pos, idx, numc, offs)
+        rt.index_down = down
+        return rt, idx, score.unsqueeze(1)
+
+    @torch.no_grad()
+    def _forward_inference(self, x, k=None, threshold=None, token_mask=None, noise=None, interpolate_pos_encoding: bool = False,
+                           token_dtype: Optional[torch.dtype] = None):
         """x: images (B, 3, H, W) (or a list of (3, H, W)).  Returns the reference's 3-tuple
         ``(group_features, idx_cluster, score)`` (tokenizer.py:182) for the whole batch: ``group_features`` is a
         RaggedTokens whose ``[b]`` is image b's (K_b, C_tok) tensor, ``idx_cluster`` is (B, N) int64 and

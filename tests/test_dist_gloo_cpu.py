@@ -89,3 +89,33 @@ def test_deal_by_cost_balances_mixed_resolutions():
     assert max(cost) <= 1.2 * sum(cost) / 8
     contiguous = [sum(s ** 2 for s in sizes[slice(*shard_batch(len(sizes), r, 8))]) for r in range(8)]
     assert max(contiguous) > 1.5 * sum(contiguous) / 8
+
+
+def _ag_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from setok_b200.training import all_gather_with_grad
+    x = (torch.arange(6, dtype=torch.float32).reshape(3, 2) + 10 * rank).requires_grad_()
+    full = all_gather_with_grad(x)
+    # a loss every rank weights differently: rank r contributes (r + 1) * sum(full * w)
+    w = torch.arange(full.numel(), dtype=torch.float32).reshape(full.shape)
+    ((rank + 1) * (full * w).sum()).backward()
+    q.put((rank, full.detach().clone(), x.grad.clone()))
+    dist.destroy_process_group()
+
+
+def test_all_gather_with_grad_world2():
+    """multilabel_constrastive.py:14-23 (diffdist all_gather): forward = concatenation over ranks, backward = the SUM over ranks of
+    the gradients that flowed into this rank's slice."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ag_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted([q.get(timeout=180) for _ in procs], key=lambda t: t[0])
+    [p.join(60) for p in procs]
+    full_exp = torch.cat([torch.arange(6, dtype=torch.float32).reshape(3, 2), torch.arange(6, dtype=torch.float32).reshape(3, 2) + 10])
+    w = torch.arange(12, dtype=torch.float32).reshape(6, 2)
+    for rank, full, grad in res:
+        assert torch.equal(full, full_exp)
+        assert torch.equal(grad, (1 + 2) * w[rank * 3:(rank + 1) * 3])
