@@ -45,8 +45,9 @@ DETOK = dict(token_feat_dim=1024, hidden_dim=768, patch_size=14, image_size=336,
 KNN_K = 16
 BATCH = 256
 SEED = 1234
-# dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch, mean of fc2/qkv/out_proj/fc1 (profiles/r01_ncu_summary.md)
-NCU_GEMM_DRAM_BYTES_PER_LAUNCH = (804.5e6 + 494.0e6 + 363.0e6 + 631.8e6) / 4
+# dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch, mean of fc2/qkv/out_proj/fc1 with the f32 residual stream
+# (profiles/r02_ncu_summary.md); the algorithmic operand bytes of the same mix are 742e6
+NCU_GEMM_DRAM_BYTES_PER_LAUNCH = (1129.8e6 + 496.8e6 + 622.8e6 + 633.3e6) / 4
 NCU_CLUSTER_DRAM_BYTES_PER_LAUNCH = 269.0e6 + 7.5e6   # dpc_fused_kernel, dram read + write (profiles/r01_ncu_summary.md)
 
 WORKLOADS = {

@@ -389,7 +389,9 @@ extern "C" int setok_detok_forward(const setok_detok* d, const void* tokens, int
       // cross-attention to the image's own K_b tokens (module.py:528-544), varlen over the packed rows
       SETOK_TRY(launch_gemm(GemmArgs{w.a, H, L.w_cq, H, w.q, H, SETOK_BF16, L.b_cq, nullptr, 0, 0, SETOK_ACT_NONE, R, H, H, nullptr, 0}, stream));
       SETOK_TRY(launch_gemm(GemmArgs{w.enc, H, L.w_ckv, H, w.kv, 2LL * H, SETOK_BF16, L.b_ckv, nullptr, 0, 0, SETOK_ACT_NONE, cap, 2 * H, H, n_tok, 0}, stream));
-      SETOK_TRY(launch_cross_attention(w.q, w.kv, w.ctx, R, Q, H, d->q_heads, qscale, offsets, stream));
+      // the tensor-core kernel's last 64-key box of the batch reaches up to 63 rows past the last live row: keep them finite
+      SETOK_TRY(launch_zero_tail_rows(w.kv, 2LL * H, n_tok, 64, cap, 2 * H, stream));
+      SETOK_TRY(launch_cross_attention(w.q, w.kv, w.ctx, R, Q, H, d->q_heads, qscale, offsets, cap, stream));
       SETOK_TRY(launch_gemm(GemmArgs{w.ctx, H, L.w_co, H, w.t32, H, SETOK_F32, L.b_co, w.a, H, SETOK_BF16, SETOK_ACT_NONE, R, H, H, nullptr, 0}, stream));
       SETOK_TRY(launch_layernorm(w.t32, SETOK_F32, w.a, SETOK_BF16, L.ln_c_g, L.ln_c_b, d->q_ln_eps, R, H, nullptr, nullptr, stream));
     }

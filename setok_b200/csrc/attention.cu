@@ -260,13 +260,18 @@ int launch_attention(const void* qkv, void* out, int rows, int C, int heads, flo
 
 // Cross-attention of `rows` = B * Q query rows (q [rows, C]) over the ragged key/value rows kv [*, 2C] (keys in columns
 // [0, C), values in [C, 2C)): query row r sees rows [offsets[r / Q], offsets[r / Q + 1]).
+int g_cross_tc = 1;   // 0: the CUDA-core kernels only (A/B timing via setok_debug_set_cross_attention_tc)
+
+// kv_rows: row capacity of `kv` (the tensor-core kernel's TMA map is bounded by it); 0 = unknown -> CUDA-core kernels
 int launch_cross_attention(const void* q, const void* kv, void* out, int rows, int Q, int C, int heads, float scale,
-                           const int32_t* offsets, cudaStream_t stream) {
+                           const int32_t* offsets, int kv_rows, cudaStream_t stream) {
   SETOK_REQUIRE(q && kv && out && offsets, SETOK_ERR_BAD_ARG, "cross_attention: null pointer");
   SETOK_REQUIRE(rows > 0 && Q > 0 && rows % Q == 0 && C > 0 && heads > 0 && C % heads == 0, SETOK_ERR_BAD_ARG, "cross_attention: bad shape rows=%d Q=%d C=%d heads=%d", rows, Q, C, heads);
   const int hd = C / heads;
   SETOK_REQUIRE(hd % 8 == 0 && hd <= 512, SETOK_ERR_UNSUPPORTED, "cross_attention: head_dim %d unsupported (need %%8==0, <=512)", hd);
   SETOK_REQUIRE(aligned16(q) && aligned16(kv) && aligned16(out), SETOK_ERR_BAD_ARG, "cross_attention: buffers must be 16-byte aligned");
+  if (hd == 64 && g_cross_tc && kv_rows > 0 && C % 8 == 0)
+    return launch_cross_attention_tcgen05(q, kv, out, rows / Q, Q, C, heads, scale, offsets, kv_rows, stream);
   if (hd == XA_HD) {
     dim3 grid(heads, rows / Q, ceil_div(Q, XA_THREADS));
     cross_attn_hd64_kernel<<<grid, XA_THREADS, 0, stream>>>(static_cast<const bf16*>(q), static_cast<const bf16*>(kv), static_cast<bf16*>(out), Q, C,
@@ -293,3 +298,5 @@ extern "C" int setok_attention(const void* qkv, void* out, int rows, int C, int 
                                const int32_t* row_seg, int uniform_T, const int32_t* m_dev, setok_stream_t stream) {
   return setok::launch_attention(qkv, out, rows, C, heads, scale, seg_off, row_seg, uniform_T, m_dev, static_cast<cudaStream_t>(stream));
 }
+
+extern "C" void setok_debug_set_cross_attention_tc(int on) { setok::g_cross_tc = on; }

@@ -41,10 +41,13 @@ __device__ __forceinline__ float fast_exp2(float x) {   // MUFU.EX2; exp2(-inf) 
   return y;
 }
 
-// declared for 256 threads so ptxas caps registers at 128: two CTAs (6 warps each) then fit the per-SMSP register files
+// CROSS = false: self-attention over qkv [B][T][3C] (keys = the image's own T rows).
+// CROSS = true : the Q-Former's cross-attention (module.py:283-364): queries q [B][T][C], keys / values the image's own rows
+//                [offsets[b], offsets[b+1]) of the packed kv [*, 2C] ([k | v]); a varlen kernel keyed by `offsets`, no padding mask.
+template <bool CROSS>
 __global__ void __launch_bounds__(ATT_THREADS, 4)
 attn_tcgen05_hd64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm_kv, bf16* __restrict__ out,
-                         int T, int heads, int C, float scale_log2, long long* __restrict__ dbg) {
+                         int T, int heads, int C, float scale_log2, long long* __restrict__ dbg, const int32_t* __restrict__ offsets) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
 #ifdef SETOK_ATTN_TRACE
   const bool trace = dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 1 && blockIdx.z == 1;
@@ -59,7 +62,6 @@ attn_tcgen05_hd64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_co
   pdl_launch_dependents();
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int q0 = qt * QT;
-  const int nchunks = (T + KT - 1) / KT;
 
   const uint32_t bar0 = base + OFF_BARS;
   const uint32_t q_full = bar0, s_full = bar0 + 8, p_full = bar0 + 16, o_final = bar0 + 24;
@@ -83,6 +85,23 @@ attn_tcgen05_hd64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_co
   const uint32_t tmem_base = *tmem_holder;
   pdl_wait();                                   // qkv comes from the previous kernel of the stream
   if (threadIdx.x == 0) TRACE(1);
+  // keys of this CTA: Tk rows starting at row krow0 of batch index kb of the key/value map; columns kcol (K) / vcol (V)
+  const int krow0 = CROSS ? offsets[b] : 0;
+  const int Tk = CROSS ? offsets[b + 1] - krow0 : T;
+  const int kb = CROSS ? 0 : b;
+  const int kcol = (CROSS ? 0 : C) + h * HD, vcol = (CROSS ? C : 2 * C) + h * HD;
+  const int nchunks = (Tk + KT - 1) / KT;
+  if (CROSS && Tk <= 0) {
+    // an image without tokens: zeros (no barrier is armed, every role falls through to the common exit)
+    if (warp < 4) {
+      const int grow = q0 + (warp & 3) * 32 + lane;
+      if (grow < T) {
+        bf16* dst = out + (static_cast<long long>(b) * T + grow) * C + h * HD;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4*>(dst + 8 * g) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+  } else
 
   if (warp == W_TMA) {
     if (lane == 0) {
@@ -92,8 +111,8 @@ attn_tcgen05_hd64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_co
         const int s = j % KV_STAGES;
         mbar_wait(kv_empty(s), ((j / KV_STAGES) & 1) ^ 1u);
         mbar_arrive_expect_tx(kv_full(s), 2 * KV_STAGE);
-        tma_load_3d(&tm_kv, kv_full(s), base + OFF_K + s * KV_STAGE, C + h * HD, j * KT, b);
-        tma_load_3d(&tm_kv, kv_full(s), base + OFF_V + s * KV_STAGE, 2 * C + h * HD, j * KT, b);
+        tma_load_3d(&tm_kv, kv_full(s), base + OFF_K + s * KV_STAGE, kcol, krow0 + j * KT, kb);
+        tma_load_3d(&tm_kv, kv_full(s), base + OFF_V + s * KV_STAGE, vcol, krow0 + j * KT, kb);
       }
     }
   } else if (warp == W_MMA) {
@@ -112,7 +131,7 @@ attn_tcgen05_hd64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_co
 #define ISSUE_S(J)                                                                                   \
       do {                                                                                             \
         const int j_ = (J);                                                                            \
-        const int nk_ = min(KT, ((T - j_ * KT) + 15) & ~15);                                           \
+        const int nk_ = min(KT, ((Tk - j_ * KT) + 15) & ~15);                                          \
         const uint32_t idesc_ = nk_ == KT ? idesc_s_full : umma_idesc_bf16(QT, nk_);                   \
         const int st_ = j_ % KV_STAGES;                                                                \
         mbar_wait(kv_full(st_), (j_ / KV_STAGES) & 1);                                                 \
@@ -132,7 +151,7 @@ attn_tcgen05_hd64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_co
       ISSUE_S(0);
       if (lane == 0) TRACE(3);
       for (int j = 0; j < nchunks; ++j) {
-        const int nk16 = min(KT, ((T - j * KT) + 15) & ~15) >> 4;
+        const int nk16 = min(KT, ((Tk - j * KT) + 15) & ~15) >> 4;
         mbar_wait(p_full, j & 1);
         if (lane == 0) TRACE(10 + 4 * j);
         tcgen05_fence_after();
@@ -163,7 +182,7 @@ attn_tcgen05_hd64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_co
       if (warp == 0 && lane == 0) TRACE(40 + 4 * j);
       tcgen05_fence_after();
       if (warp_live) {
-        const int valid = min(KT, T - j * KT);        // real keys in this chunk (columns >= valid hold stale data)
+        const int valid = min(KT, Tk - j * KT);       // real keys in this chunk (columns >= valid hold stale data)
         float m_new, alpha, psum;
         // S row (64 fp32) read from TMEM once; the probabilities are packed to bf16 pairs in place and stored back to
         // TMEM over the first 32 S columns, where the P.V MMA reads them as its A operand (no trip through smem)
@@ -292,10 +311,39 @@ int launch_attention_tcgen05(const void* qkv, void* out, int B, int T, int C, in
   r = enc(&tm_kv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(qkv), gdim, gstr, box_kv, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(SETOK_ERR_CUDA, "attention: cuTensorMapEncodeTiled (kv) failed with CUresult %d", (int)r);
-  SETOK_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(attn_tcgen05_hd64_kernel), ATT_SMEM));
+  SETOK_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(attn_tcgen05_hd64_kernel<false>), ATT_SMEM));
   dim3 grid(ceil_div(T, QT), heads, B);
-  SETOK_CUDA_OK(launch_pdl(attn_tcgen05_hd64_kernel, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tm, tm_kv, static_cast<bf16*>(out), T, heads, C,
-                           scale * 1.4426950408889634f, g_attn_trace));
+  SETOK_CUDA_OK(launch_pdl(attn_tcgen05_hd64_kernel<false>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tm, tm_kv, static_cast<bf16*>(out), T, heads, C,
+                           scale * 1.4426950408889634f, g_attn_trace, static_cast<const int32_t*>(nullptr)));
+  SETOK_LAUNCH_CHECK();
+  return SETOK_OK;
+}
+
+// Varlen cross-attention on the tensor cores: q bf16 [B*Q, C], kv bf16 [kv_rows (capacity), 2C] = [k | v], query rows of image b
+// see kv rows [offsets[b], offsets[b+1]); heads of 64.  Rows of a 64-key chunk past the image's last key belong to the next image
+// (or to the zeroed tail, see launch_zero_tail_rows) and are masked: they never reach the softmax, and P = 0 meets finite V.
+int launch_cross_attention_tcgen05(const void* q, const void* kv, void* out, int B, int Q, int C, int heads, float scale,
+                                   const int32_t* offsets, int kv_rows, cudaStream_t stream) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return fail(SETOK_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  CUtensorMap tm, tm_kv;
+  cuuint32_t estr[3] = {1, 1, 1};
+  cuuint64_t qdim[3] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(Q), static_cast<cuuint64_t>(B)};
+  cuuint64_t qstr[2] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(Q) * C * 2};
+  cuuint32_t box[3] = {HD, QT, 1};
+  CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(q), qdim, qstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SETOK_ERR_CUDA, "cross attention: cuTensorMapEncodeTiled (q) failed with CUresult %d", (int)r);
+  cuuint64_t kdim[3] = {static_cast<cuuint64_t>(2 * C), static_cast<cuuint64_t>(kv_rows), 1};
+  cuuint64_t kstr[2] = {static_cast<cuuint64_t>(2 * C) * 2, static_cast<cuuint64_t>(kv_rows) * 2 * C * 2};
+  cuuint32_t box_kv[3] = {HD, KT, 1};
+  r = enc(&tm_kv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(kv), kdim, kstr, box_kv, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SETOK_ERR_CUDA, "cross attention: cuTensorMapEncodeTiled (kv) failed with CUresult %d", (int)r);
+  SETOK_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(attn_tcgen05_hd64_kernel<true>), ATT_SMEM));
+  dim3 grid(ceil_div(Q, QT), heads, B);
+  SETOK_CUDA_OK(launch_pdl(attn_tcgen05_hd64_kernel<true>, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tm, tm_kv, static_cast<bf16*>(out), Q, heads, C,
+                           scale * 1.4426950408889634f, static_cast<long long*>(nullptr), offsets));
   SETOK_LAUNCH_CHECK();
   return SETOK_OK;
 }

@@ -441,6 +441,8 @@ int launch_attention_fullrow(const void* qkv, void* out, int B, int T, int C, in
 int launch_attention(const void* qkv, void* out, int rows, int C, int heads, float scale, const int32_t* seg_off,
                      const int32_t* row_seg, int uniform_T, const int32_t* m_dev, cudaStream_t stream);
 int launch_cross_attention(const void* q, const void* kv, void* out, int rows, int Q, int C, int heads, float scale,
-                           const int32_t* offsets, cudaStream_t stream);
+                           const int32_t* offsets, int kv_rows, cudaStream_t stream);
+int launch_cross_attention_tcgen05(const void* q, const void* kv, void* out, int B, int Q, int C, int heads, float scale,
+                                   const int32_t* offsets, int kv_rows, cudaStream_t stream);
 
 }  // namespace setok

@@ -342,6 +342,14 @@ __global__ void __launch_bounds__(256) masked_softmax_kernel(const float* __rest
   }
 }
 
+__global__ void zero_tail_rows_kernel(bf16* __restrict__ buf, long long ld, const int32_t* __restrict__ n_live_dev, int n_rows, int cap, int cols) {
+  const int n0 = min(max(*n_live_dev, 0), cap);
+  const int n1 = min(n0 + n_rows, cap);
+  const int total = (n1 - n0) * cols;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
+    buf[static_cast<long long>(n0 + i / cols) * ld + i % cols] = __float2bfloat16_rn(0.f);
+}
+
 inline int grid_for(long long work_items, int threads, int max_waves = 8) {
   long long blocks = (work_items + threads - 1) / threads;
   const long long cap = static_cast<long long>(num_sms()) * max_waves;
@@ -448,6 +456,12 @@ int launch_select_rows(const void* x, int x_dtype, void* out, int out_dtype, int
   if (x_dtype == SETOK_BF16) { if (out_dtype == SETOK_F32) SETOK_SEL(bf16, float); else SETOK_SEL(bf16, bf16); }
   else { if (out_dtype == SETOK_F32) SETOK_SEL(float, float); else SETOK_SEL(float, bf16); }
 #undef SETOK_SEL
+  SETOK_LAUNCH_CHECK();
+  return SETOK_OK;
+}
+
+int launch_zero_tail_rows(void* buf_bf16, long long ld, const int32_t* n_live_dev, int n_rows, int cap, int cols, cudaStream_t stream) {
+  zero_tail_rows_kernel<<<grid_for(static_cast<long long>(n_rows) * cols, 256), 256, 0, stream>>>(static_cast<bf16*>(buf_bf16), ld, n_live_dev, n_rows, cap, cols);
   SETOK_LAUNCH_CHECK();
   return SETOK_OK;
 }

@@ -39,3 +39,30 @@ fl_d = DEPTH * (24 * Q * Dd * Dd + 4 * Q * Q * Dd) + 2 * Q * H * Dd
 flops = B * (fl_q + fl_d) + ncross * total * (4 * H * H + 4 * Q / 1 * 0) + 2 * total * CT * H
 print(f"detokenizer B={B} Q={Q} hidden={H} dec={Dd}x{DEPTH}: {ms:.2f} ms  {B / ms * 1e3:.0f} images/s  {flops / ms / 1e9:.0f} TFLOP/s "
       f"(sum K = {total}, K mean {total / B:.1f})")
+
+# A/B: the CUDA-core cross-attention kernel against the tensor-core one (default), same inputs, outputs compared
+import ctypes
+from setok_b200 import _lib
+lib = _lib.load()
+lib.setok_debug_set_cross_attention_tc.argtypes = [ctypes.c_int]
+lib.setok_debug_set_cross_attention_tc.restype = None
+
+
+def timed():
+    for _ in range(2):
+        o = det(rt)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        o = det(rt)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps, o.float()
+
+
+lib.setok_debug_set_cross_attention_tc(0)
+ms_cc, o_cc = timed()
+lib.setok_debug_set_cross_attention_tc(1)
+ms_tc, o_tc = timed()
+err = float((o_tc - o_cc).norm() / o_cc.norm())
+print(f"cross-attention A/B: CUDA-core {ms_cc:.2f} ms, tcgen05 {ms_tc:.2f} ms per detokenizer call; outputs differ by {err:.2e} rel-Frobenius")
