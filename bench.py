@@ -411,7 +411,9 @@ class Harness:
 
     def timed_e2e(self, run_steps):
         args = self.args
-        nbytes = run_steps(3)
+        # warm-up with as many steps as the timed region: the pipeline keeps several batches in flight, and the pinned-host /
+        # device caching allocators must have seen that depth before the clock starts (a first cudaHostAlloc blocks the device)
+        nbytes = run_steps(max(3, args.warmup, args.steps))
         self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

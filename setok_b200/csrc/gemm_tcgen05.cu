@@ -53,13 +53,15 @@ struct GemmDev {
   long long d_batch_stride;   // elements of D's type
   long long r_batch_stride;   // elements of the residual's type
   int w_mn_major;
+  int direct;                 // row-owner epilogue without the shared-memory transpose (see the epilogue branch)
   int epi_mode;               // debug (setok_debug_set_gemm_epi_mode): 0 normal; 1 drain only (no transpose / math / stores);
-                              // 2 transpose + math, no residual loads / stores; 3 normal minus the residual loads
+                              // 2 transpose + math, no residual loads / stores; 3 normal minus the residual loads; 4 / 5: drain only and the
+                              // producer stages A only / nothing (is the main loop bound by L2->SM operand traffic?)
 };
 
 // Epilogue configuration is a template so the per-element code has no run-time branches; -1 = run time
 // (the generic instantiation serves the rarely used combinations).
-template <int CG, int ACT, int RES, int OUTF32, int REMAP>
+template <int CG, int ACT, int RES, int OUTF32, int REMAP, bool DIRECT>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmDev p) {
   constexpr int STAGES = Cfg<CG>::STAGES, B_STAGE_BYTES = Cfg<CG>::B_STAGE_BYTES, STAGE_BYTES = Cfg<CG>::STAGE_BYTES;
@@ -122,7 +124,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = base + OFF_A + stage * A_STAGE_BYTES, sb = base + OFF_B + stage * B_STAGE_BYTES;
-          if (CG == 2) {
+          if (p.epi_mode >= 4) {
+            // diagnostic (tools/bench_gemm_modes.py): mode 4 stages A only, mode 5 nothing -- the MMAs run on stale smem, so
+            // the time left is the tensor pipe's (plus A's share of the L2 traffic in mode 4)
+            if (CG == 2) {
+              const uint32_t lead_full = mapa_shared(full_bar(stage), 0);
+              if (p.epi_mode == 4) {
+                if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * A_STAGE_BYTES);
+                tma_load_3d_2sm(&tmA, lead_full, sa, kb * BK, a_row, bt);
+              } else if (rank == 0) {
+                mbar_arrive(full_bar(stage));
+              }
+            } else if (p.epi_mode == 4) {
+              mbar_arrive_expect_tx(full_bar(stage), A_STAGE_BYTES);
+              tma_load_3d(&tmA, full_bar(stage), sa, kb * BK, a_row, bt);
+            } else {
+              mbar_arrive(full_bar(stage));
+            }
+          } else if (CG == 2) {
             // both CTAs' bytes are counted on the LEADER's full barrier (the MMA issuer waits there).  The peer cannot
             // run a phase ahead: its empty barrier for this stage fires only after the MMAs that consumed the stage
             // retired, i.e. after the leader's full barrier already flipped.
@@ -182,6 +201,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
     }
   } else {
+    static_assert(!DIRECT || (ACT >= 0 && RES >= 0 && OUTF32 >= 0 && REMAP == 0), "row-owner epilogue: specialised instantiations only");
     const int act = ACT >= 0 ? ACT : p.act;
     const int res_kind = RES >= 0 ? RES : p.res_kind;
     const bool out_f32 = OUTF32 >= 0 ? (OUTF32 != 0) : (p.out_f32 != 0);
@@ -201,6 +221,86 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const long long dbase = static_cast<long long>(bt) * p.d_batch_stride;
       bool waited = false;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + half * 128);
+      if constexpr (DIRECT) {
+        // Row-owner epilogue: thread `lane` keeps TMEM lane (= tile row) q*32+lane and writes its 32 columns of every chunk
+        // straight from registers with 256-bit stores -- one full 32-byte sector per thread per instruction -- so the tile
+        // never crosses shared memory (whose bandwidth the TMA writes and the MMA operand reads already fill) and there
+        // is no intra-warp synchronisation.  The next chunk's tcgen05.ld is in flight while this one is processed.
+        const int grow = row0 + lane;
+        const bool row_ok = grow < M_eff;
+        constexpr int RW = RES == 1 ? 16 : 32;                 // residual words per chunk and thread
+        constexpr int DW = OUTF32 ? 32 : 16;                   // output words per chunk and thread
+        uint32_t rres[RES != 0 ? 2 : 1][RES != 0 ? RW : 1];
+        const char* rptr = nullptr;
+        if (RES != 0) rptr = static_cast<const char*>(p.res) + (static_cast<long long>(bt) * p.r_batch_stride + static_cast<long long>(grow) * p.ldr + n0) * (RES == 1 ? 2 : 4);
+        char* dptr = static_cast<char*>(p.D) + (dbase + static_cast<long long>(grow) * p.ldd + n0) * (OUTF32 ? 4 : 2);
+        auto load_res = [&](int ch, int slot) {
+          if (RES != 0) {
+            const bool ok = row_ok && (n0 + ch * 32 < p.N);
+#pragma unroll
+            for (int v = 0; v < RW / 8; ++v) {
+              if (ok) ld_global_v8(rptr + ch * (RW * 4) + v * 32, &rres[slot][8 * v]);
+              else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) rres[slot][8 * v + e] = 0u;
+              }
+            }
+          }
+        };
+        if (RES != 0 && p.epi_mode == 0) { load_res(0, 0); load_res(1, 1); }
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tcgen05_fence_after();
+        // accumulator chunks: double-buffered (the next tcgen05.ld in flight under this chunk's math and stores) unless the
+        // f32 residual ring already takes 64 registers (3 warps share an SM sub-partition: 168 registers per thread)
+        constexpr int NB = RES == 2 ? 1 : 2;
+        uint32_t ra[NB][32];
+        tmem_ld_32x32b_x32(taddr, ra[0]);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const int gcol0 = n0 + ch * 32;
+          tmem_ld_wait();
+          if (NB == 2 && ch + 1 < 4) tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, ra[(ch + 1) % NB]);
+          uint32_t* a = ra[ch % NB];
+          if (gcol0 >= p.N || p.epi_mode == 1) {
+            if (NB == 1 && ch + 1 < 4) tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, ra[0]);
+            continue;
+          }
+          uint32_t* outw = a;           // results replace the accumulator words in place (word 2c / 4c is consumed before it is rewritten)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(bias + gcol0) + c);
+            float v[4] = {__uint_as_float(a[4 * c]) + b4.x, __uint_as_float(a[4 * c + 1]) + b4.y,
+                          __uint_as_float(a[4 * c + 2]) + b4.z, __uint_as_float(a[4 * c + 3]) + b4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (ACT == SETOK_ACT_QUICK_GELU) v[e] = act_quick_gelu(v[e]);
+              else if (ACT == SETOK_ACT_GELU_ERF) v[e] = act_gelu_erf(v[e]);
+            }
+            if (RES == 1) {
+              const float2 lo = unpack_bf16x2(rres[ch & 1][2 * c]), hi = unpack_bf16x2(rres[ch & 1][2 * c + 1]);
+              v[0] += lo.x; v[1] += lo.y; v[2] += hi.x; v[3] += hi.y;
+            } else if (RES == 2) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[e] += __uint_as_float(rres[ch & 1][4 * c + e]);
+            }
+            if (OUTF32) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) outw[4 * c + e] = __float_as_uint(v[e]);
+            } else {
+              outw[2 * c] = pack_bf16x2(v[0], v[1]);
+              outw[2 * c + 1] = pack_bf16x2(v[2], v[3]);
+            }
+          }
+          if (RES != 0 && ch + 2 < 4 && p.epi_mode == 0) load_res(ch + 2, ch & 1);
+          if (row_ok && p.epi_mode != 2) {
+#pragma unroll
+            for (int v = 0; v < DW / 8; ++v) st_global_v8(dptr + ch * (DW * 4) + v * 32, &outw[8 * v]);
+          }
+          if (NB == 1 && ch + 1 < 4) tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, ra[0]);
+        }
+        waited = true;
+      } else {
       // Residual of the ViT's out_proj / fc2 (x += ...): requested ahead of its use so that the HBM latency overlaps the
       // MMAs instead of being paid once per 32-column chunk.  bf16: the whole tile (4 chunks, 64 registers) before waiting
       // for the accumulator; f32: a ring of two chunks (64 registers), chunk c + 2 requested when chunk c has been consumed.
@@ -271,7 +371,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         uint32_t r0[32];
         tmem_ld_32x32b_x32(taddr + ch * 32, r0);
         tmem_ld_wait();
-        if (epi_mode == 1) continue;
+        if (epi_mode == 1 || epi_mode >= 4) continue;
         // transpose through smem: thread `lane` owns tile row q*32+lane, 32 fp32 columns (8 x 16 B, XOR-swizzled)
 #pragma unroll
         for (int c = 0; c < 8; ++c)
@@ -308,6 +408,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
         __syncwarp();
       }
+      }   // transposing epilogue
       if (!waited) { mbar_wait(tfull_bar(acc), acc_phase); tcgen05_fence_after(); }
       tcgen05_fence_before();
       __syncwarp();
@@ -365,6 +466,7 @@ int make_tmap_bf16(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t col
 }  // namespace
 
 int g_gemm_epi_mode = 0;
+int g_gemm_epi_direct = -1;   // -1 automatic, 0 / 1 force the transposing / the row-owner epilogue (setok_debug_set_gemm_epi_direct)
 int g_gemm_cta_group = 0;   // 0 = automatic; 1 forces single-CTA tiles (debug / A-B timing via setok_debug_set_gemm_cta_group)
 
 int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
@@ -392,22 +494,35 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, GemmDev);
   const int res_kind = g.residual ? (g.residual_dtype == SETOK_BF16 ? 1 : 2) : 0;
   const int out_f32 = g.out_dtype == SETOK_F32 ? 1 : 0;
+  // Row-owner epilogue (no shared-memory transpose): needs whole 32-column chunks and 32-byte aligned rows of the output /
+  // residual.  Measured at the ViT-L shapes (tools/bench_gemm_epilogue.py, B200, M = 65792): bf16 outputs gain 2-25 % (qkv
+  // -4 %, fc1 -7 %, GELU(erf) fc1 -10 %, bf16-stream out_proj -25 %, fc2 -2 %); float32 outputs written 32 bytes per row and
+  // instruction lose on the HBM-bound K = 1024 shape (f32-stream out_proj +25 %, plain f32 output +5 %) and gain 3 % at
+  // K = 4096 (fc2): the automatic choice follows those measurements.
+  bool direct = g.N % 32 == 0 && (g_gemm_epi_direct == 1 || (g_gemm_epi_direct < 0 && (!out_f32 || (res_kind == 2 && g.K >= 2048))));
+  {
+    const int de = out_f32 ? 4 : 2, re = res_kind == 1 ? 2 : 4;
+    direct = direct && (g.ldd * de) % 32 == 0 && (reinterpret_cast<uintptr_t>(g.D) % 32) == 0 && (g.d_batch_stride * de) % 32 == 0;
+    if (g.residual) direct = direct && (g.ldr * re) % 32 == 0 && (reinterpret_cast<uintptr_t>(g.residual) % 32) == 0 && (g.r_batch_stride * re) % 32 == 0;
+  }
   // specialised epilogues for the combinations the tokenizer path launches; everything else -> generic
   // CTA pairs whenever there is at least one full 256-row tile; single CTAs for short row counts
   const int cg = (g.M >= 160 && g_gemm_cta_group != 1) ? 2 : 1;
-#define SETOK_PICK(A, R, O, P) (cg == 2 ? gemm_bf16_tcgen05_kernel<2, A, R, O, P> : gemm_bf16_tcgen05_kernel<1, A, R, O, P>)
+#define SETOK_PICK(A, R, O, P) (cg == 2 ? gemm_bf16_tcgen05_kernel<2, A, R, O, P, false> : gemm_bf16_tcgen05_kernel<1, A, R, O, P, false>)
+#define SETOK_PICK_D(A, R, O) (direct ? (cg == 2 ? gemm_bf16_tcgen05_kernel<2, A, R, O, 0, true> : gemm_bf16_tcgen05_kernel<1, A, R, O, 0, true>) : SETOK_PICK(A, R, O, 0))
   KernelFn fn = SETOK_PICK(-1, -1, -1, -1);
   if (g.remap_P == 0) {
-    if (g.act == SETOK_ACT_NONE && res_kind == 0 && !out_f32) fn = SETOK_PICK(0, 0, 0, 0);              // qkv
-    else if (g.act == SETOK_ACT_NONE && res_kind == 1 && !out_f32) fn = SETOK_PICK(0, 1, 0, 0);         // ViT out_proj / fc2
-    else if (g.act == SETOK_ACT_QUICK_GELU && res_kind == 0 && !out_f32) fn = SETOK_PICK(1, 0, 0, 0);   // ViT fc1
-    else if (g.act == SETOK_ACT_GELU_ERF && res_kind == 0 && !out_f32) fn = SETOK_PICK(2, 0, 0, 0);     // head / projector fc1
-    else if (g.act == SETOK_ACT_NONE && res_kind == 2 && out_f32) fn = SETOK_PICK(0, 2, 1, 0);          // head proj / fc2
-    else if (g.act == SETOK_ACT_NONE && res_kind == 0 && out_f32) fn = SETOK_PICK(0, 0, 1, 0);          // out / projector last
-    else if (g.act == SETOK_ACT_NONE && res_kind == 1 && out_f32) fn = SETOK_PICK(0, 1, 1, 0);          // Q-Former dense + residual -> post-LN
+    if (g.act == SETOK_ACT_NONE && res_kind == 0 && !out_f32) fn = SETOK_PICK_D(0, 0, 0);              // qkv
+    else if (g.act == SETOK_ACT_NONE && res_kind == 1 && !out_f32) fn = SETOK_PICK_D(0, 1, 0);         // bf16-stream out_proj / fc2
+    else if (g.act == SETOK_ACT_QUICK_GELU && res_kind == 0 && !out_f32) fn = SETOK_PICK_D(1, 0, 0);   // ViT fc1
+    else if (g.act == SETOK_ACT_GELU_ERF && res_kind == 0 && !out_f32) fn = SETOK_PICK_D(2, 0, 0);     // head / projector / decoder fc1
+    else if (g.act == SETOK_ACT_NONE && res_kind == 2 && out_f32) fn = SETOK_PICK_D(0, 2, 1);          // f32-stream out_proj / fc2, head proj / fc2
+    else if (g.act == SETOK_ACT_NONE && res_kind == 0 && out_f32) fn = SETOK_PICK_D(0, 0, 1);          // out / projector last
+    else if (g.act == SETOK_ACT_NONE && res_kind == 1 && out_f32) fn = SETOK_PICK_D(0, 1, 1);          // Q-Former dense + residual -> post-LN
   } else if (g.act == SETOK_ACT_NONE && res_kind == 2 && out_f32) {
     fn = SETOK_PICK(0, 2, 1, 1);                                                                         // patch embedding
   }
+#undef SETOK_PICK_D
 #undef SETOK_PICK
   const int smem_bytes = cg == 2 ? Cfg<2>::SMEM_BYTES : Cfg<1>::SMEM_BYTES;
   SETOK_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(fn), smem_bytes));
@@ -424,6 +539,7 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   p.remap_P = g.remap_P;
   p.batch = g.batch; p.d_batch_stride = g.d_batch_stride; p.r_batch_stride = g.r_batch_stride; p.w_mn_major = g.w_mn_major;
   p.epi_mode = g_gemm_epi_mode;
+  p.direct = direct ? 1 : 0;
   const int tiles = ceil_div(g.M, BM * cg) * ceil_div(g.N, BN) * g.batch;
   const int max_groups = num_sms() / cg;
   const int grid = (tiles < max_groups ? tiles : max_groups) * cg;
@@ -464,3 +580,4 @@ extern "C" int setok_gemm_bf16_batched(const void* A, int64_t lda, int64_t a_bat
 
 extern "C" void setok_debug_set_gemm_cta_group(int cg) { setok::g_gemm_cta_group = cg; }
 extern "C" void setok_debug_set_gemm_epi_mode(int mode) { setok::g_gemm_epi_mode = mode; }
+extern "C" void setok_debug_set_gemm_epi_direct(int v) { setok::g_gemm_epi_direct = v; }

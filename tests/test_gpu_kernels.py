@@ -68,6 +68,49 @@ def test_gemm_epilogues(act, res):
         _close(out, ref, 5e-3 if res == torch.bfloat16 else 1e-4, "in-place residual")
 
 
+@pytest.mark.parametrize("act,res,odt", [(ops.ACT_NONE, None, torch.bfloat16), (ops.ACT_QUICK_GELU, None, torch.bfloat16),
+                                         (ops.ACT_GELU_ERF, None, torch.bfloat16), (ops.ACT_NONE, torch.bfloat16, torch.bfloat16),
+                                         (ops.ACT_NONE, torch.float32, torch.float32), (ops.ACT_NONE, None, torch.float32),
+                                         (ops.ACT_NONE, torch.bfloat16, torch.float32)])
+@pytest.mark.parametrize("M,N,K", [(391, 512, 256), (2056, 1024, 2048), (77, 96, 64), (1, 32, 8), (700, 3072, 1024)])
+def test_gemm_row_owner_epilogue_equals_transposing_epilogue(act, res, odt, M, N, K):
+    """The two epilogues of the tcgen05 GEMM (shared-memory transpose + coalesced stores / row-owner 256-bit stores) perform
+    the same float operations in the same order: their outputs must be bit-identical, ragged rows, in-place residual and the
+    device-side row count included, and rows past the live count stay untouched."""
+    import ctypes
+    from setok_b200 import _lib
+    lib = _lib.load()
+    lib.setok_debug_set_gemm_epi_direct.argtypes = [ctypes.c_int]
+    lib.setok_debug_set_gemm_epi_direct.restype = None
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(DEV, torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) * K ** -0.5).to(DEV, torch.bfloat16)
+    bias = torch.randn(N, generator=g).to(DEV)
+    r = None if res is None else torch.randn(M, N, generator=g).to(DEV, res)
+    live = max(1, M - 37)
+    m_dev = torch.tensor([live], dtype=torch.int32, device=DEV)
+    outs = []
+    try:
+        for mode in (0, 1):
+            lib.setok_debug_set_gemm_epi_direct(mode)
+            full = ops.gemm(a, w, bias, act=act, residual=r, out_dtype=odt)
+            part = torch.full((M, N), -7.0, device=DEV, dtype=odt)
+            ops.gemm(a, w, bias, act=act, residual=r, out=part, m_dev=m_dev)
+            inplace = None
+            if r is not None and res == odt:
+                inplace = r.clone()
+                ops.gemm(a, w, bias, act=act, residual=inplace, out=inplace)
+            outs.append((full, part, inplace))
+    finally:
+        lib.setok_debug_set_gemm_epi_direct(-1)
+    (f0, p0, i0), (f1, p1, i1) = outs
+    assert torch.equal(f0, f1) and torch.equal(p0, p1)
+    assert torch.equal(p1[:live], f1[:live]) and bool((p1[live:] == -7.0).all())
+    if i0 is not None:
+        assert torch.equal(i0, i1) and torch.equal(i1, f1)
+    _close(f1, _gemm_ref(a, w, bias, act, r), 1e-4 if odt == torch.float32 else 5e-3, "row-owner epilogue")
+
+
 def test_gemm_device_row_count_and_untouched_tail():
     M, N, K = 1000, 256, 128
     g = torch.Generator().manual_seed(9)

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Decomposes the tcgen05 GEMM's time at the ViT-L layer shapes by switching parts of the epilogue off
 (setok_debug_set_gemm_epi_mode): 0 normal, 1 drain only (MMA + TMA + TMEM loads), 2 + smem transpose + math (no global traffic),
-3 normal minus the residual loads.  bf16 and f32 residual streams.  GPU only."""
+3 normal minus the residual loads, 4 drain only + the producer stages A only, 5 drain only + no operand loads at all
+(stale shared memory: the tensor pipe's own rate at the clocks the power cap allows).  bf16 and f32 residual streams.  GPU only."""
 import ctypes
 import os
 import sys
@@ -39,18 +40,18 @@ def main():
     shapes = [("qkv", a, 3 * C, C, ops.ACT_NONE, None), ("fc1", a, F, C, ops.ACT_QUICK_GELU, None),
               ("out_proj/bf16", a, C, C, ops.ACT_NONE, xb), ("out_proj/f32", a, C, C, ops.ACT_NONE, xf),
               ("fc2/bf16", u, C, F, ops.ACT_NONE, xb), ("fc2/f32", u, C, F, ops.ACT_NONE, xf)]
-    print(f"{'shape':14s} " + " ".join(f"mode{m:d}_us" for m in range(4)) + "   TFLOP/s(mode0)  TFLOP/s(mode1)")
+    print(f"{'shape':14s} " + " ".join(f"mode{m:d}_us" for m in range(6)) + "   TFLOP/s(mode0)  TFLOP/s(mode1)  TFLOP/s(mode5)")
     for name, inp, n, k, act, res in shapes:
         w = (torch.randn(n, k, device=dev, generator=g) * k ** -0.5).to(torch.bfloat16)
         b = torch.zeros(n, device=dev)
         out = res if res is not None else torch.empty(M, n, dtype=torch.bfloat16, device=dev)
         ts = []
-        for mode in range(4):
+        for mode in range(6):
             lib.setok_debug_set_gemm_epi_mode(mode)
             ts.append(timeit(lambda: ops.gemm(inp, w, b, act=act, residual=res, out=out)))
         lib.setok_debug_set_gemm_epi_mode(0)
         fl = 2.0 * M * n * k
-        print(f"{name:14s} " + " ".join(f"{t * 1e3:8.1f}" for t in ts) + f"   {fl / ts[0] / 1e9:8.1f}  {fl / ts[1] / 1e9:8.1f}")
+        print(f"{name:14s} " + " ".join(f"{t * 1e3:8.1f}" for t in ts) + f"   {fl / ts[0] / 1e9:8.1f}  {fl / ts[1] / 1e9:8.1f}  {fl / ts[5] / 1e9:8.1f}")
     # LayerNorm passes: bf16 -> bf16 and f32 -> bf16
     gam, bet = torch.ones(C, device=dev), torch.zeros(C, device=dev)
     for nm, src in (("bf16", xb), ("f32", xf)):
