@@ -345,6 +345,22 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, bool b_mn_m
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// kind::f16 with IEEE half operands (A / B format fields 0) -- otherwise as umma_idesc_bf16
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, bool b_mn_major = false) {
+  return (1u << 4) | (b_mn_major ? (1u << 16) : 0u) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+// two floats -> packed IEEE halves (round to nearest, finite saturation: |x| > 65504 clamps instead of becoming inf)
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t u) {
+  float2 f;
+  asm("{ .reg .b16 l, h; mov.b32 {l, h}, %2; cvt.f32.f16 %0, l; cvt.f32.f16 %1, h; }" : "=f"(f.x), "=f"(f.y) : "r"(u));
+  return f;
+}
+
 // ---- CTA pairs (cta_group::2): cluster helpers, peer-barrier signalling, 2-SM TMA / MMA / TMEM forms -----------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

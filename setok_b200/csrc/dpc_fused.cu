@@ -31,26 +31,33 @@
 #include <cmath>
 
 namespace setok {
-int g_dpc_fused = 1;   // 0: multi-kernel path only; 1: fused, 4-term split; 2: fused, 3-term split (lo.lo dropped)
+// 0: multi-kernel path only; 1: fused, IEEE-half hi/lo split, 3 terms (default); 2: fused, bf16 split, 4 terms; 3: fused, bf16
+// split, 3 terms (lo.lo dropped)
+int g_dpc_fused = 1;
 namespace {
 
 constexpr int FZ_BK = 64;                              // channels per operand stage
 constexpr int FZ_OP_STAGES = 2;
-constexpr int FZ_RAW_STAGES = 2;
+constexpr int FZ_RAW_STAGES = 3;
 constexpr int FZ_TILE_BYTES = 256 * 128;               // 32 KiB: 256 rows x 128 B (64 bf16 | 32 fp32)
 constexpr int FZ_OP_STAGE_BYTES = 2 * FZ_TILE_BYTES;   // hi tile + lo tile
 constexpr int FZ_ROW_WARPS = 8;
+constexpr int FZ_GROUP_WARPS = 4;                      // the row warps convert in two groups that take alternate half-stages
 constexpr int FZ_ROW_THREADS = 32 * FZ_ROW_WARPS;
 constexpr int FZ_W_MMA = FZ_ROW_WARPS, FZ_W_TMA = FZ_ROW_WARPS + 1;
 constexpr int FZ_THREADS = FZ_ROW_THREADS + 64;
 constexpr int FZ_OFF_RAW = FZ_OP_STAGES * FZ_OP_STAGE_BYTES;
-constexpr int FZ_OFF_ARR = FZ_OFF_RAW + FZ_RAW_STAGES * FZ_TILE_BYTES;
-// float sqn[256], dens[256], rmax[256], score[256], maskv[256]; int cidx[256]; int wcount[8]; uint cmask[8]; float red[8]
+// The select phase's arrays (float sqn[256], dens[256], rmax[256], score[256], maskv[256]; int cidx[256]; int wcount[8]; uint
+// cmask[8]; float red[8]) live on top of the operand ring: they are touched only between the accumulator-complete barrier
+// (every MMA that read the ring has retired) and the select phase's last barrier (the next image's converters start after it).
+constexpr int FZ_OFF_ARR = 0;
 constexpr int FZ_ARR_BYTES = 6 * 256 * 4 + 3 * 8 * 4;
-constexpr int FZ_OFF_BAR = FZ_OFF_ARR + FZ_ARR_BYTES;
+static_assert(FZ_ARR_BYTES <= FZ_OP_STAGE_BYTES, "select arrays must fit the operand ring");
+constexpr int FZ_OFF_BAR = FZ_OFF_RAW + FZ_RAW_STAGES * FZ_TILE_BYTES;
 constexpr int FZ_HALVES = 2 * FZ_OP_STAGES;           // half-stages (32 channels): the unit of the operand pipeline
 constexpr int FZ_NUM_BARS = 2 * FZ_HALVES + 2 * FZ_RAW_STAGES + 2;
 constexpr int FZ_SMEM_BYTES = FZ_OFF_BAR + FZ_NUM_BARS * 8 + 16 + 1024;
+static_assert(FZ_SMEM_BYTES <= 232448, "dpc_fused: shared memory over the 227 KiB a CTA may use");
 
 struct FusedDev {
   const float* pos;
@@ -61,7 +68,7 @@ struct FusedDev {
   float* score;
   int64_t* index_down;
   int32_t* num_clusters;
-  int B, N, C, k, min_cluster_num, terms;
+  int B, N, C, k, min_cluster_num, terms, f16;
   float threshold, sqrtC, inv_sqrtC;   // inv_sqrtC > 0 when sqrt(C) is a power of two (x / 2^e == x * 2^-e exactly)
 };
 
@@ -192,8 +199,10 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) dpc_fused_kernel(const __grid_c
   volatile uint32_t* tmem_holder = reinterpret_cast<volatile uint32_t*>(smem + FZ_OFF_BAR + FZ_NUM_BARS * 8);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < FZ_HALVES; ++s) { mbar_init(full_bar(s), FZ_ROW_WARPS); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < FZ_RAW_STAGES; ++s) { mbar_init(rfull_bar(s), 1); mbar_init(rempty_bar(s), FZ_ROW_WARPS); }
+    // a half-stage is written by ONE converter group; a raw tile is read by one group (fp32: 32 channels = one half-stage) or
+    // by both (bf16: 64 channels = two half-stages)
+    for (int s = 0; s < FZ_HALVES; ++s) { mbar_init(full_bar(s), FZ_GROUP_WARPS); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < FZ_RAW_STAGES; ++s) { mbar_init(rfull_bar(s), 1); mbar_init(rempty_bar(s), FBF16 ? FZ_ROW_WARPS : FZ_GROUP_WARPS); }
     mbar_init(tfull_bar, 1);
     mbar_init(tempty_bar, FZ_ROW_WARPS);
     fence_mbar_init();
@@ -234,7 +243,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) dpc_fused_kernel(const __grid_c
   } else if (warp == FZ_W_MMA) {
     // ------------------------------------------------ MMA issuer ------------------------------------------------
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, Npad);
+      const uint32_t idesc = p.f16 ? umma_idesc_f16(128, Npad) : umma_idesc_bf16(128, Npad);
       int stage = 0; uint32_t phase = 0, it = 0;
       for (int b = blockIdx.x; b < p.B; b += gridDim.x, ++it) {
         mbar_wait(tempty_bar, (it & 1u) ^ 1u);           // the row warps are done with the previous image's D
@@ -270,123 +279,126 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) dpc_fused_kernel(const __grid_c
     const int i = warp * 32 + lane;                      // this thread's token in the select phase
     const bool active = i < N;
     const uint32_t trow = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + static_cast<uint32_t>((warp >> 2) * 256);
-    // convert-phase lane mapping: a unit = 8 channels of one row; a half-stage = operand chunks 4h..4h+3 (32 channels) of
-    // all rows = one fp32 raw tile or half a bf16 raw tile; 4 lanes cover a row's half, 8 rows per warp, 64 rows per pass
+    // convert-phase mapping: the 8 row warps form two groups of 4; group g takes the half-stages hs = g, g + 2, ... (32 channels
+    // of all rows each), so that one group's chain (wait raw tile -> shared loads -> split -> operand stores -> proxy fence ->
+    // publish) runs under the other's.  A unit = 8 channels of one row; 4 lanes cover a row's 32 channels, 8 rows per warp,
+    // 32 rows per pass of a group, MT * 4 units per thread and half-stage.
+    const int grp = warp >> 2, gw = warp & 3;
     const int c4 = lane & 3, rsub = lane >> 2;
-    constexpr int PR = FZ_ROW_WARPS * 8;                 // rows per pass: a multiple of 8
-    const int passes = MT * 128 / PR;                    // 2 | 4
-    const int r0 = warp * 8 + rsub;                      // this thread's row in pass 0; (row & 7) is the same in every pass
+    constexpr int PR = FZ_GROUP_WARPS * 8;               // rows per pass of one group: a multiple of 8
+    const int units = MT * 128 / PR;                     // 4 | 8
+    const int r0 = gw * 8 + rsub;                        // this thread's row in pass 0; (row & 7) is the same in every pass
     const int x7 = r0 & 7;
     const bool has_mask = p.token_mask != nullptr;
     const bool has_pos = p.pos != nullptr;
-    int stage = 0, rs = 0; uint32_t phase = 0, rphase = 0, it = 0;
-    for (int b = blockIdx.x; b < p.B; b += gridDim.x, ++it) {
+    const int HS = 2 * k_blocks;                         // half-stages per image (even: both groups take HS / 2 of them)
+    uint32_t gh_base = 0, it = 0;                        // half-stages of this CTA's earlier images
+    for (int b = blockIdx.x; b < p.B; b += gridDim.x, ++it, gh_base += static_cast<uint32_t>(HS)) {
       // ---- (1) convert: raw tile (+ pos) -> hi/lo operand tiles ----
       const long long img = static_cast<long long>(b) * N * C;
-      // half-stages hs = 2 * kb + h in order; the position embedding of half-stage hs+1 is requested (L2-resident table,
-      // plain loads) before half-stage hs is processed
-      const int HS = 2 * k_blocks;
-      auto load_pos = [&](int hs, float4 (&pa)[4], float4 (&pb)[4]) {
-        if (!has_pos || hs >= HS) return;
-        int ch = (hs >> 1) * FZ_BK + ((hs & 1) * 4 + c4) * 8;
-        ch = ch < C ? ch : C - 8;
-        const float* pp = p.pos + ch;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          int r = r0 + u * PR;
-          r = r < N ? r : N - 1;
-          pa[u] = __ldg(reinterpret_cast<const float4*>(pp + r * C));
-          pb[u] = __ldg(reinterpret_cast<const float4*>(pp + r * C + 4));
-        }
-      };
-      auto do_half = [&](int hs, const float4 (&pa)[4], const float4 (&pb)[4]) {
-        if (hs >= HS) return;
+#pragma unroll 1
+      for (int hs = grp; hs < HS; hs += 2) {
+        const uint32_t gh = gh_base + static_cast<uint32_t>(hs);            // position in the CTA-wide half-stage sequence
+        const int stage = static_cast<int>(gh & (FZ_HALVES - 1));
+        const uint32_t phase = (gh / FZ_HALVES) & 1u;
+        const uint32_t t = FBF16 ? (gh >> 1) : gh;                           // raw tile in the CTA-wide sequence
+        const int rs = static_cast<int>(t % FZ_RAW_STAGES);
+        const uint32_t rphase = (t / FZ_RAW_STAGES) & 1u;
         const int h = hs & 1;
+        const int oc = h * 4 + c4;                       // 16-byte chunk of the operand row (8 halves)
+        const int ch = (hs >> 1) * FZ_BK + oc * 8;
+        // position embedding of this thread's units (L2-resident table): requested before the waits
+        float4 pa[8], pb[8];
+        if (has_pos) {
+          const float* pp = p.pos + (ch < C ? ch : C - 8);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            if (u < units) {
+              int r = r0 + u * PR;
+              r = r < N ? r : N - 1;
+              pa[u] = __ldg(reinterpret_cast<const float4*>(pp + r * C));
+              pb[u] = __ldg(reinterpret_cast<const float4*>(pp + r * C + 4));
+            }
+          }
+        }
         mbar_wait(empty_bar(stage), phase ^ 1u);
         if (threadIdx.x == 0) FZ_TRACE(1, 3 * hs);
-        if (!FBF16 || h == 0) mbar_wait(rfull_bar(rs), rphase);
+        mbar_wait(rfull_bar(rs), rphase);
         if (threadIdx.x == 0) FZ_TRACE(1, 3 * hs + 1);
-        const int oc = h * 4 + c4;                       // 16-byte chunk of the operand row (8 bf16)
         uint8_t* hi_t = smem + (stage >> 1) * FZ_OP_STAGE_BYTES + r0 * 128 + ((oc ^ x7) << 4);
         const uint8_t* raw_t = smem + FZ_OFF_RAW + rs * FZ_TILE_BYTES + r0 * 128;
-        // all shared-memory reads first (the compiler cannot move them across the operand stores below)
-        uint4 qa[4], qb[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (FBF16) {
-            qa[u] = *reinterpret_cast<const uint4*>(raw_t + u * PR * 128 + ((oc ^ x7) << 4));
-          } else {
-            qa[u] = *reinterpret_cast<const uint4*>(raw_t + u * PR * 128 + (((2 * c4) ^ x7) << 4));
-            qb[u] = *reinterpret_cast<const uint4*>(raw_t + u * PR * 128 + (((2 * c4 + 1) ^ x7) << 4));
+        for (int ub = 0; ub < 8; ub += 4) {
+          if (ub < units) {
+            // the shared-memory reads of four units first (the compiler cannot move them across the operand stores below)
+            uint4 qa[4], qb[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (FBF16) {
+                qa[u] = *reinterpret_cast<const uint4*>(raw_t + (ub + u) * PR * 128 + ((oc ^ x7) << 4));
+              } else {
+                qa[u] = *reinterpret_cast<const uint4*>(raw_t + (ub + u) * PR * 128 + (((2 * c4) ^ x7) << 4));
+                qb[u] = *reinterpret_cast<const uint4*>(raw_t + (ub + u) * PR * 128 + (((2 * c4 + 1) ^ x7) << 4));
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int r = r0 + (ub + u) * PR;
+              float v[8];
+              if (FBF16) {
+                const float2 a = unpack_bf16x2(qa[u].x), c2 = unpack_bf16x2(qa[u].y), e2 = unpack_bf16x2(qa[u].z), g2 = unpack_bf16x2(qa[u].w);
+                v[0] = a.x; v[1] = a.y; v[2] = c2.x; v[3] = c2.y; v[4] = e2.x; v[5] = e2.y; v[6] = g2.x; v[7] = g2.y;
+              } else {
+                v[0] = __uint_as_float(qa[u].x); v[1] = __uint_as_float(qa[u].y); v[2] = __uint_as_float(qa[u].z); v[3] = __uint_as_float(qa[u].w);
+                v[4] = __uint_as_float(qb[u].x); v[5] = __uint_as_float(qb[u].y); v[6] = __uint_as_float(qb[u].z); v[7] = __uint_as_float(qb[u].w);
+              }
+              if (has_pos) {
+                const float4 a4 = pa[ub + u], b4 = pb[ub + u];
+                v[0] = __fadd_rn(v[0], a4.x); v[1] = __fadd_rn(v[1], a4.y); v[2] = __fadd_rn(v[2], a4.z); v[3] = __fadd_rn(v[3], a4.w);
+                v[4] = __fadd_rn(v[4], b4.x); v[5] = __fadd_rn(v[5], b4.y); v[6] = __fadd_rn(v[6], b4.z); v[7] = __fadd_rn(v[7], b4.w);
+              }
+              if (!(r < N && ch < C)) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = 0.f;
+              } else if (p.x_pos != nullptr) {
+                float* xo = p.x_pos + img + static_cast<long long>(r) * C + ch;
+                *reinterpret_cast<float4*>(xo) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(xo + 4) = make_float4(v[4], v[5], v[6], v[7]);
+              }
+              uint32_t hh[4], ll[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float x0 = v[2 * q], x1 = v[2 * q + 1];
+                if (p.f16) {
+                  hh[q] = pack_f16x2_sat(x0, x1);
+                  const float2 hf = unpack_f16x2(hh[q]);
+                  ll[q] = pack_f16x2_sat(x0 - hf.x, x1 - hf.y);
+                } else {
+                  hh[q] = pack_bf16x2(x0, x1);
+                  const float2 hf = unpack_bf16x2(hh[q]);
+                  ll[q] = pack_bf16x2(x0 - hf.x, x1 - hf.y);
+                }
+              }
+              *reinterpret_cast<uint4*>(hi_t + (ub + u) * PR * 128) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+              *reinterpret_cast<uint4*>(hi_t + FZ_TILE_BYTES + (ub + u) * PR * 128) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+            }
           }
         }
-        const int ch = (hs >> 1) * FZ_BK + oc * 8;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (u < passes) {
-            const int r = r0 + u * PR;
-            float v[8];
-            if (FBF16) {
-              const float2 a = unpack_bf16x2(qa[u].x), c2 = unpack_bf16x2(qa[u].y), e2 = unpack_bf16x2(qa[u].z), g2 = unpack_bf16x2(qa[u].w);
-              v[0] = a.x; v[1] = a.y; v[2] = c2.x; v[3] = c2.y; v[4] = e2.x; v[5] = e2.y; v[6] = g2.x; v[7] = g2.y;
-            } else {
-              v[0] = __uint_as_float(qa[u].x); v[1] = __uint_as_float(qa[u].y); v[2] = __uint_as_float(qa[u].z); v[3] = __uint_as_float(qa[u].w);
-              v[4] = __uint_as_float(qb[u].x); v[5] = __uint_as_float(qb[u].y); v[6] = __uint_as_float(qb[u].z); v[7] = __uint_as_float(qb[u].w);
-            }
-            if (has_pos) {
-              v[0] = __fadd_rn(v[0], pa[u].x); v[1] = __fadd_rn(v[1], pa[u].y); v[2] = __fadd_rn(v[2], pa[u].z); v[3] = __fadd_rn(v[3], pa[u].w);
-              v[4] = __fadd_rn(v[4], pb[u].x); v[5] = __fadd_rn(v[5], pb[u].y); v[6] = __fadd_rn(v[6], pb[u].z); v[7] = __fadd_rn(v[7], pb[u].w);
-            }
-            if (!(r < N && ch < C)) {
-#pragma unroll
-              for (int q = 0; q < 8; ++q) v[q] = 0.f;
-            } else if (p.x_pos != nullptr) {
-              float* xo = p.x_pos + img + static_cast<long long>(r) * C + ch;
-              *reinterpret_cast<float4*>(xo) = make_float4(v[0], v[1], v[2], v[3]);
-              *reinterpret_cast<float4*>(xo + 4) = make_float4(v[4], v[5], v[6], v[7]);
-            }
-            uint32_t hh[4], ll[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float x0 = v[2 * q], x1 = v[2 * q + 1];
-              hh[q] = pack_bf16x2(x0, x1);
-              const float2 hf = unpack_bf16x2(hh[q]);
-              ll[q] = pack_bf16x2(x0 - hf.x, x1 - hf.y);
-            }
-            *reinterpret_cast<uint4*>(hi_t + u * PR * 128) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-            *reinterpret_cast<uint4*>(hi_t + FZ_TILE_BYTES + u * PR * 128) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
-          }
-        }
-        if (!FBF16 || h == 1) {
-          // raw tile read -> back to the producer
-          __syncwarp();
-          if (lane == 0) mbar_arrive(rempty_bar(rs));
-          if (++rs == FZ_RAW_STAGES) { rs = 0; rphase ^= 1u; }
-        }
+        // this warp is done with the raw tile (fp32: the tile was this group's alone; bf16: the other group reads its other half)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(rempty_bar(rs));
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(full_bar(stage));
         if (threadIdx.x == 0) FZ_TRACE(1, 3 * hs + 2);
-        if (++stage == FZ_HALVES) { stage = 0; phase ^= 1u; }
-      };
-      {
-        float4 paA[4], pbA[4], paB[4], pbB[4];
-        load_pos(0, paA, pbA);
-#pragma unroll 1
-        for (int hs = 0; hs < HS; hs += 2) {
-          load_pos(hs + 1, paB, pbB);
-          do_half(hs, paA, pbA);
-          load_pos(hs + 2, paA, pbA);
-          do_half(hs + 1, paB, pbB);
-        }
       }
-      if (has_mask && active) maskv_s[i] = p.token_mask[static_cast<long long>(b) * N + i];
 
       // ---- (2) select on the accumulator ----
       if (threadIdx.x == 0) FZ_TRACE(2, 0);
       mbar_wait(tfull_bar, it & 1u);
       tcgen05_fence_after();
       if (threadIdx.x == 0) FZ_TRACE(2, 1);
+      if (has_mask && active) maskv_s[i] = p.token_mask[static_cast<long long>(b) * N + i];
       {
         // row norms = Gram diagonal (see the header)
         uint32_t r[32];
@@ -570,7 +582,12 @@ int launch_dpc_fused(const void* feats, int feat_dtype, const float* pos, const 
   p.pos = pos; p.noise = noise; p.token_mask = token_mask; p.x_pos = x_pos; p.idx_cluster = idx_cluster;
   p.score = score; p.index_down = index_down; p.num_clusters = num_clusters;
   p.B = B; p.N = N; p.C = C; p.k = k; p.min_cluster_num = min_cluster_num; p.threshold = threshold;
-  p.terms = (g_dpc_fused & 3) == 2 ? 3 : 4;
+  // Operand split of the exact Gram (x = hi + lo): IEEE halves carry 11 + 11 significand bits, so hi hi^T + hi lo^T + lo hi^T
+  // leaves out only lo lo^T <= 2^-22 |x_i x_j| (below the float32 rounding of the product itself) -- 3 MMAs per k-step and a
+  // tighter representation than the bf16 pair (8 + 8 bits, 2^-17 |x|, which needs all 4 terms).  Domain: |x| <= 65504
+  // (finite saturation beyond; CLIP features + sincos table are O(1) .. O(1e2)).
+  p.f16 = (g_dpc_fused & 3) == 1 ? 1 : 0;
+  p.terms = (g_dpc_fused & 3) == 2 ? 4 : 3;
   if (g_dpc_fused & 8) p.x_pos = nullptr;    // timing experiments only
   if (g_dpc_fused & 16) p.pos = nullptr;
   p.sqrtC = static_cast<float>(std::sqrt(static_cast<double>(C)));

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Clustering (a3+a4) A/B: multi-kernel path vs the fused persistent kernel (4-term / 3-term split), agreement of
+"""Clustering (a3+a4) A/B: multi-kernel path vs the fused persistent kernel (IEEE-half 3-term split = default, bf16 4-term, bf16 3-term), agreement of
 their integer outputs, and timings at the BASELINE config-2 shape.  GPU only."""
 import ctypes
 import os
@@ -57,7 +57,7 @@ def accuracy():
     rel = lambda s: ((s.double() - truth).abs() / truth.abs().clamp_min(1e-9))
     e = rel(ref32)
     print(f"accuracy vs fp64 truth (B={B}, k={k}):  torch fp32 reference formula: max {float(e.max()):.2e} mean {float(e.mean()):.2e}")
-    for mode in (0, 1, 2, 5, 6):
+    for mode in (0, 1, 2, 3):
         lib.setok_debug_set_dpc_fused(mode)
         out = ops.dpc_cluster(feats, noise, (N, 1), k, 0.5, 64, pos_table=zero_pos)
         e = rel(out[2])
@@ -72,7 +72,7 @@ def main():
         feats = mog_features(B, N, C, 7, dev).to(dtype)
         noise = torch.rand(B, N, device=dev)
         outs = {}
-        for mode, name in ((0, "multi-kernel"), (1, "fused 4-term"), (2, "fused 3-term"), (6, "fused 3t diag")):
+        for mode, name in ((0, "multi-kernel"), (1, "fused f16 3t"), (2, "fused bf16 4t"), (3, "fused bf16 3t")):
             lib.setok_debug_set_dpc_fused(mode)
             for k in (16, 64):
                 run = lambda: ops.dpc_cluster(feats, noise, (16, 16), k, 0.5, 64)
@@ -86,7 +86,7 @@ def main():
                       f"{int(Kc.min())}/{float(Kc.mean()):.1f}/{int(Kc.max())}")
         for k in (16, 64):
             ref = outs[(0, k)]
-            for mode in (1, 2, 6):
+            for mode in (1, 2, 3):
                 o = outs[(mode, k)]
                 same_k = int((o[4] == ref[4]).sum())
                 same_lab = float((o[1] == ref[1]).float().mean())
