@@ -69,6 +69,7 @@ struct FusedDev {
   int64_t* index_down;
   int32_t* num_clusters;
   int B, N, C, k, min_cluster_num, terms, f16;
+  int dbg;                             // timing experiments (setok_debug_set_dpc_fused bits 5, 6): 1 converters touch no shared memory, 2 + no TMA loads
   float threshold, sqrtC, inv_sqrtC;   // inv_sqrtC > 0 when sqrt(C) is a power of two (x / 2^e == x * 2^-e exactly)
 };
 
@@ -232,6 +233,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) dpc_fused_kernel(const __grid_c
 #ifdef SETOK_FZ_TRACE
           { const unsigned it = (b == (int)blockIdx.x) ? 0u : 1u; FZ_TRACE(3, t); }
 #endif
+          if (p.dbg == 2) { mbar_arrive(rfull_bar(rs)); if (++rs == FZ_RAW_STAGES) { rs = 0; rphase ^= 1u; } continue; }
           mbar_arrive_expect_tx(rfull_bar(rs), FZ_TILE_BYTES);
           // 256-row box starting at the image's first row: for N < 256 the tail rows belong to the next image (or are
           // zero-filled past the end of the tensor) and are discarded by the converters
@@ -329,7 +331,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) dpc_fused_kernel(const __grid_c
         const uint8_t* raw_t = smem + FZ_OFF_RAW + rs * FZ_TILE_BYTES + r0 * 128;
 #pragma unroll
         for (int ub = 0; ub < 8; ub += 4) {
-          if (ub < units) {
+          if (ub < units && p.dbg == 0) {
             // the shared-memory reads of four units first (the compiler cannot move them across the operand stores below)
             uint4 qa[4], qb[4];
 #pragma unroll
@@ -587,6 +589,7 @@ int launch_dpc_fused(const void* feats, int feat_dtype, const float* pos, const 
   // tighter representation than the bf16 pair (8 + 8 bits, 2^-17 |x|, which needs all 4 terms).  Domain: |x| <= 65504
   // (finite saturation beyond; CLIP features + sincos table are O(1) .. O(1e2)).
   p.f16 = (g_dpc_fused & 3) == 1 ? 1 : 0;
+  p.dbg = (g_dpc_fused >> 5) & 3;
   p.terms = (g_dpc_fused & 3) == 2 ? 4 : 3;
   if (g_dpc_fused & 8) p.x_pos = nullptr;    // timing experiments only
   if (g_dpc_fused & 16) p.pos = nullptr;
