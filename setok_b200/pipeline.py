@@ -37,7 +37,11 @@ class HostResult:
 class _Readback:
     """D2H of one batch's ragged result on a dedicated stream.  The row count is data-dependent, so the read-back is two
     hops (offsets, then the packed rows) unless the host already knows the offsets (a gathered batch); both wait only for
-    THIS batch's kernels (an event), never for the batch the main stream is already running, and land in pinned memory."""
+    THIS batch's kernels (an event), never for the batch the main stream is already running, and land in pinned memory.
+
+    The device tensors are kept alive by this object until `result()` has synchronised with the copies (no
+    `Tensor.record_stream`: a recorded block is not reusable until the allocator has polled the side stream's event, which
+    made every step cudaMalloc a fresh capacity-sized buffer -- 134 MB for config 4's projected rows -- inside the step)."""
 
     def __init__(self, out, d2h: torch.cuda.Stream, after: torch.cuda.Event):
         self.rt, self.idx, self.score = out
@@ -45,8 +49,6 @@ class _Readback:
         d2h.wait_event(after)
         known = self.rt._host is not None            # offsets already on the host (RaggedAllGather.finish)
         with torch.cuda.stream(d2h):
-            for t in (self.rt.data, self.rt.offsets, self.idx, self.score):
-                t.record_stream(d2h)
             self.h_off = torch.empty(self.rt.offsets.shape, dtype=self.rt.offsets.dtype, pin_memory=True)
             self.h_off.copy_(self.rt.offsets, non_blocking=True)
             self.h_idx = torch.empty(self.idx.shape, dtype=self.idx.dtype, pin_memory=True)
@@ -64,13 +66,36 @@ class _Readback:
         h_tok.copy_(self.rt.data[:total], non_blocking=True)
         return h_tok
 
+    def _release(self):
+        self.rt = self.idx = self.score = None        # the copies are complete: the blocks go back to their own stream's pool
+
     def result(self) -> HostResult:
         self.ev.synchronize()
         if self.h_tok is None:
             with torch.cuda.stream(self.d2h):
                 self.h_tok = self._rows(int(self.h_off[-1]))
             self.d2h.synchronize()
+        self._release()
         return HostResult(self.h_tok, self.h_off, self.h_idx, self.h_score)
+
+    def __del__(self):                                # abandoned before result(): the copies may still be reading the tensors
+        try:
+            if getattr(self, "rt", None) is not None:
+                self.d2h.synchronize()
+        except Exception:
+            pass
+
+
+_side_streams = {}
+
+
+def _streams(dev: torch.device):
+    """One copy stream and one read-back stream per device for the life of the process: the caching allocators keep a pool
+    per stream, so a fresh stream per call would cudaMalloc its input buffers again on every call."""
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _side_streams:
+        _side_streams[key] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+    return _side_streams[key]
 
 
 def stream_tokenize(tokenizer, host_batches: Iterable[Tuple[torch.Tensor, Optional[torch.Tensor]]],
@@ -79,8 +104,7 @@ def stream_tokenize(tokenizer, host_batches: Iterable[Tuple[torch.Tensor, Option
     batch, in order.  `post(ragged, idx, score) -> (ragged, idx, score)` runs on the device right after the tokenizer (e.g.
     the projector); `gather` (dist.RaggedAllGather) then repacks the ranks' ragged outputs into the global batch."""
     dev = tokenizer.device
-    copy_stream = torch.cuda.Stream(dev)
-    d2h_stream = torch.cuda.Stream(dev)
+    copy_stream, d2h_stream = _streams(dev)
     main = torch.cuda.current_stream(dev)
 
     def upload(batch):
