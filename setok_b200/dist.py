@@ -79,7 +79,10 @@ class RaggedAllGather:
             self.comm = comm
             comm.wait_event(produced)
             with torch.cuda.stream(comm):
-                for t in (hdr, hdr_all, local.data):
+                # (the packed rows are NOT record_stream'ed: a recorded block of capacity size -- 268 MB for a 256-image batch --
+                # would not be reusable until the allocator has polled this stream, i.e. a cudaMalloc per step; the handle and
+                # then the gathered result keep `local` alive until the row exchange that reads it has been ordered)
+                for t in (hdr, hdr_all):
                     t.record_stream(comm)
                 dist.all_gather_into_tensor(hdr_all, hdr, group=self.group)
                 # pinned host copy of the gathered header, so that finish() waits on an event instead of the device
@@ -157,6 +160,10 @@ class RaggedAllGather:
         out = RaggedTokens(data, offsets, down)
         out._host = [int(v) for v in offs.tolist()]     # the host already knows the offsets: per-image slicing needs no sync
         out.ready = ready
+        # the row all-gather reads `local` on the communication stream: `local` lives at least as long as the result.  With
+        # wait=True the current stream waits for `ready`, so nothing launched afterwards can reuse its block early; with
+        # wait=False the caller keeps the result until it has ordered itself after `ready` (pipeline._Readback does).
+        out._keep = local
         if ready is not None and wait:
             cur = torch.cuda.current_stream(dev)
             cur.wait_event(ready)
