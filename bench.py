@@ -47,8 +47,8 @@ BATCH = 256
 SEED = 1234
 # dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch, mean of fc2/qkv/out_proj/fc1 with the f32 residual stream
 # (profiles/r02_ncu_summary.md); the algorithmic operand bytes of the same mix are 742e6
-NCU_GEMM_DRAM_BYTES_PER_LAUNCH = (1129.8e6 + 496.8e6 + 622.8e6 + 633.3e6) / 4
-NCU_CLUSTER_DRAM_BYTES_PER_LAUNCH = 269.0e6 + 7.5e6   # dpc_fused_kernel, dram read + write (profiles/r01_ncu_summary.md)
+NCU_GEMM_DRAM_BYTES_PER_LAUNCH = (1109.2e6 + 497.3e6 + 623.5e6 + 634.5e6) / 4
+NCU_CLUSTER_DRAM_BYTES_PER_LAUNCH = 268.8e6 + 5.9e6   # dpc_fused_kernel, dram read + write (profiles/r02_ncu_summary.md)
 
 WORKLOADS = {
     2: "BASELINE config 2: batch 256 synthetic 224^2 Mondrian images per GPU, ViT-L/14 (23 of 24 layers, select_layer -2), "
@@ -290,6 +290,21 @@ def cuda_time_graph(fn, reps, warm=3):
         return cuda_time(fn, reps, warm=1), f"eager loop (graph capture failed: {type(exc).__name__})"
 
 
+def cuda_time_single(fn, n=9, idle_s=0.01):
+    """Median device time of ONE call issued after the GPU has been idle (boost clocks, as under ncu): events bracket a single call."""
+    ts = []
+    for _ in range(n):
+        torch.cuda.synchronize()
+        time.sleep(idle_s)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return statistics.median(ts)
+
+
 def time_gemm_mix(dev, layers_run, rows, reps=2):
     """Average launch duration of the dominant kernel (the tcgen05 GEMM) over the ViT's real launch mix, measured
     with CUDA events on the launching stream: per layer qkv / out_proj / fc1 / fc2 at M = batch * T rows, f32 residual
@@ -329,10 +344,11 @@ def time_cluster(dev, reps=20):
     ms, how = cuda_time_graph(lambda: ops.dpc_cluster(feats, noise, (16, 16), KNN_K, 0.5, 64, embedded=True), reps)
     ms_eager = cuda_time(lambda: ops.dpc_cluster(feats, noise, (16, 16), KNN_K, 0.5, 64, embedded=True), reps, warm=1)
     out = ops.dpc_cluster(feats, noise, (16, 16), KNN_K, 0.5, 64, embedded=True)
+    ms_single = cuda_time_single(lambda: ops.dpc_cluster(feats, noise, (16, 16), KNN_K, 0.5, 64, embedded=True))
     ms_pos, _ = cuda_time_graph(lambda: ops.dpc_cluster(feats, noise, (16, 16), KNN_K, 0.5, 64), reps)
     K = out[4].float()
     alg_bytes = BATCH * (N * C * 4 + N * 8 + N * 4 + N * 4) + float(K.sum()) * 8      # SURVEY §8d per-image figure x batch
-    return ms, alg_bytes, alg_bytes / (ms * 1e-3) / 1e9, (float(K.min()), float(K.mean()), float(K.max())), ms_pos, ms_eager, how
+    return ms, alg_bytes, alg_bytes / (ms * 1e-3) / 1e9, (float(K.min()), float(K.mean()), float(K.max())), ms_pos, ms_eager, how, ms_single
 
 
 def gpu_eager_baseline(dev, tok, images, noise, head_sample=16):
@@ -508,7 +524,7 @@ def run_config2(args):
     pk = peaks()
     vit_ms = cuda_time(lambda: tok.image_feature_encoder(images), 5)
     vit_tf = BATCH * vit_flops_per_image(layers_run) / (vit_ms * 1e-3) / 1e12
-    cl_ms, cl_bytes, cl_gbs, kstats, cl_ms_pos, cl_ms_eager, cl_how = time_cluster(dev, reps=20)
+    cl_ms, cl_bytes, cl_gbs, kstats, cl_ms_pos, cl_ms_eager, cl_how, cl_ms_single = time_cluster(dev, reps=20)
     gemm_ms, gemm_flops, gemm_tf = time_gemm_mix(dev, layers_run, BATCH * 257)
     step_ms = ms / args.steps
     line = {
@@ -523,7 +539,7 @@ def run_config2(args):
         "clocks": clocks,
         "roofline": {"kernel": "gemm_bf16_tcgen05_kernel (ViT layer launch mix: qkv/out_proj/fc1/fc2 at M=65792, f32 residual stream)", "bound": "tensor",
                      "achieved": gemm_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": gemm_tf / pk["tf_sustained"],
-                     "traffic": NCU_GEMM_DRAM_BYTES_PER_LAUNCH, "traffic_source": "ncu --set full dram__bytes_read+write, mean over the 4 shapes (profiles/r01_ncu_summary.md); algorithmic operand bytes are 607e6",
+                     "traffic": NCU_GEMM_DRAM_BYTES_PER_LAUNCH, "traffic_source": "ncu --set full dram__bytes_read+write, mean over the 4 shapes (profiles/r02_ncu_summary.md); algorithmic operand bytes are 742e6 with the f32 residual stream",
                      "flops_per_launch": gemm_flops, "ms_per_launch": gemm_ms,
                      "peak_source": f"{pk['src']} sustained bf16 (kernel timed inside a long loop)",
                      "step_share": (4 * layers_run * gemm_ms) / step_ms,
@@ -534,7 +550,10 @@ def run_config2(args):
         "roofline_cluster": {"kernel": "dpc_fused_kernel (a4 on the position-embedded tensor; a3 is fused into the tower's last row pass), B=256 N=256 C=1024 feature-injected", "bound": "hbm",
                              "achieved": cl_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": cl_gbs / pk["hbm"], "traffic": NCU_CLUSTER_DRAM_BYTES_PER_LAUNCH,
                              "bytes_per_launch": cl_bytes, "ms_per_launch": cl_ms, "timing": cl_how + " of the clustering call (dpc_fused_kernel + the offsets scan)",
-                             "ms_per_call_eager_loop": cl_ms_eager, "with_pos_ms": cl_ms_pos, "k_min_mean_max": kstats,
+                             "ms_per_call_eager_loop": cl_ms_eager, "ms_single_call_after_idle": cl_ms_single,
+                             "frac_single_call_after_idle": (cl_bytes / (cl_ms_single * 1e-3) / 1e9) / pk["hbm"],
+                             "note": "achieved / frac: back-to-back calls (the SM clock settles at the power-capped level of the rest of the step); "
+                                     "the single call after idle runs at boost clocks like the ncu capture (profiles/r02_ncu_summary.md: 130 us, 0.32)", "with_pos_ms": cl_ms_pos, "k_min_mean_max": kstats,
                              "tensor_frac_if_compute": (BATCH * 2.0 * 256 * 256 * 1024 / (cl_ms * 1e-3) / 1e12) / pk["tf_burst"],
                              "tensor_frac_executed": (3 * BATCH * 2.0 * 256 * 256 * 1024 / (cl_ms * 1e-3) / 1e12) / pk["tf_burst"]},
     }
