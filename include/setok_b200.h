@@ -96,6 +96,8 @@ typedef struct {
   const void* w_fc2;   /* bf16 [C, F] */
   const float* b_fc2;
   const float* ln1_g; const float* ln1_b; const float* ln2_g; const float* ln2_b;
+  /* SETOK_VIT_LN_FOLD only (else NULL): f32 [3C] / [F], s_n = sum_k W'_nk of the gamma-scaled bf16 matrices (see the flag) */
+  const float* s_qkv; const float* s_fc1;
 } setok_vit_layer;
 
 typedef struct {
@@ -116,6 +118,14 @@ typedef struct {
  * K = 3*Kp (pixel.w = hi.w_hi + lo.w_hi + hi.w_lo): its rounding error, which the residual stream carries unchanged
  * through every layer, drops from 2^-9 to ~2^-17 relative for 0.4 % more tower FLOPs. */
 #define SETOK_VIT_PATCH_SPLIT 2
+/* The layers' LayerNorms folded into the GEMMs around them (needs SETOK_VIT_RESIDUAL_F32 and hidden % 32 == 0): no
+ * normalisation pass re-reads the residual stream.  out_proj / fc2 also emit xhat = bf16((x - c) * r) -- x normalised with the
+ * row statistics of one sub-layer earlier -- and per-row partial sums; qkv / fc1 multiply xhat by W' = gamma (.) W and finish
+ * the LayerNorm exactly in their fp32 epilogue (gemm_tcgen05.cu).  With this flag the caller packs, per layer:
+ *   w_qkv = bf16(W_qkv * ln1_g[None, :]), b_qkv = W_qkv ln1_b + b_qkv (f32), s_qkv[n] = sum_k float(w_qkv[n, k]);
+ *   w_fc1 = bf16(W_fc1 * ln2_g[None, :]), b_fc1 = W_fc1 ln2_b + b_fc1,       s_fc1[n] = sum_k float(w_fc1[n, k]);
+ * ln1_g .. ln2_b are not read. */
+#define SETOK_VIT_LN_FOLD 4
 
 size_t setok_vit_workspace_bytes(const setok_vit* vit, int B);
 /* images (device) [B,3,H,W] f32|bf16 -> features (device) [B, N(+1), C] f32|bf16.

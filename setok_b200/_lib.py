@@ -23,7 +23,7 @@ class SetokError(RuntimeError):
 
 class VitLayer(C.Structure):
     _fields_ = [(n, c_void_p) for n in ("w_qkv", "b_qkv", "w_o", "b_o", "w_fc1", "b_fc1", "w_fc2", "b_fc2",
-                                        "ln1_g", "ln1_b", "ln2_g", "ln2_b")]
+                                        "ln1_g", "ln1_b", "ln2_g", "ln2_b", "s_qkv", "s_fc1")]
 
 
 class Vit(C.Structure):
@@ -34,7 +34,8 @@ class Vit(C.Structure):
 
 VIT_RESIDUAL_F32 = 1
 VIT_PATCH_SPLIT = 2
-ABI_VERSION = 2
+VIT_LN_FOLD = 4
+ABI_VERSION = 3
 
 
 class Attn(C.Structure):

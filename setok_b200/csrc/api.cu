@@ -11,7 +11,10 @@ using namespace setok;
 
 namespace {
 
-struct VitBufs { bf16* A; float* emb; void* x; bf16 *h, *qkv, *ao, *u; };   // x: bf16, or f32 with SETOK_VIT_RESIDUAL_F32
+struct VitBufs { bf16* A; float* emb; void* x; bf16 *h, *qkv, *ao, *u; float* rec[2]; };   // x: bf16, or f32 with SETOK_VIT_RESIDUAL_F32
+
+// SETOK_VIT_LN_FOLD: per-row record of the folded LayerNorms {c, r, (s1, s2) x ceil(C / 128)} (gemm_tcgen05.cu)
+inline size_t ln_rec_floats(int C) { return 2 + 2 * static_cast<size_t>(ceil_div(C, 128)); }
 
 int vit_carve(const setok_vit* v, int B, Arena& a, VitBufs* o) {
   const int P = (v->image_size / v->patch) * (v->image_size / v->patch);
@@ -26,6 +29,11 @@ int vit_carve(const setok_vit* v, int B, Arena& a, VitBufs* o) {
   o->qkv = a.take<bf16>(R * 3 * C);
   o->ao = a.take<bf16>(R * C);
   o->u = a.take<bf16>(R * v->mlp);
+  o->rec[0] = o->rec[1] = nullptr;
+  if (v->flags & SETOK_VIT_LN_FOLD) {
+    o->rec[0] = a.take<float>(R * ln_rec_floats(C));
+    o->rec[1] = a.take<float>(R * ln_rec_floats(C));
+  }
   return SETOK_OK;
 }
 
@@ -37,6 +45,8 @@ int check_vit(const setok_vit* v) {
                 "vit: hidden %d / heads %d unsupported", v->hidden, v->heads);
   SETOK_REQUIRE(v->mlp > 0 && v->mlp % 8 == 0 && v->layers >= 0, SETOK_ERR_UNSUPPORTED, "vit: mlp %d layers %d unsupported", v->mlp, v->layers);
   SETOK_REQUIRE(v->w_patch && v->cls && v->pos && v->pre_ln_g && v->pre_ln_b && (v->layers == 0 || v->layer), SETOK_ERR_BAD_ARG, "vit: null weights");
+  SETOK_REQUIRE(!(v->flags & SETOK_VIT_LN_FOLD) || ((v->flags & SETOK_VIT_RESIDUAL_F32) && v->hidden % 32 == 0 && v->mlp % 32 == 0), SETOK_ERR_UNSUPPORTED,
+                "vit: SETOK_VIT_LN_FOLD needs SETOK_VIT_RESIDUAL_F32 and hidden / mlp multiples of 32 (hidden %d, mlp %d)", v->hidden, v->mlp);
   return SETOK_OK;
 }
 
@@ -52,6 +62,28 @@ int run_preln_layer(const setok_vit_layer& L, void* x, int xdt, bf16* h, bf16* q
   SETOK_TRY(launch_layernorm(x, xdt, h, SETOK_BF16, L.ln2_g, L.ln2_b, eps, R, C, nullptr, nullptr, stream));
   SETOK_TRY(launch_gemm(GemmArgs{h, C, L.w_fc1, C, u, F, SETOK_BF16, L.b_fc1, nullptr, 0, 0, act, R, F, C, nullptr, 0}, stream));
   SETOK_TRY(launch_gemm(GemmArgs{u, F, L.w_fc2, F, x, C, xdt, L.b_fc2, x, C, xdt, SETOK_ACT_NONE, R, C, F, nullptr, 0}, stream));
+  return SETOK_OK;
+}
+
+// The same layer with its two LayerNorms folded into the GEMMs (SETOK_VIT_LN_FOLD): `h` holds xhat of the current stream and
+// rec[0] its row records on entry and on exit; out_proj writes the stream, xhat and rec[1], fc2 the stream, xhat and rec[0].
+// emit_next = false (the last layer run): fc2 only writes the stream.
+int run_preln_layer_fold(const setok_vit_layer& L, float* x, bf16* h, bf16* qkv, bf16* ao, bf16* u, float* const rec[2], int R, int T, int C, int F,
+                         int heads, float eps, int act, bool emit_next, cudaStream_t stream) {
+  const float scale = 1.0f / std::sqrt(static_cast<float>(C / heads));
+  GemmArgs g1{h, C, L.w_qkv, C, qkv, 3LL * C, SETOK_BF16, L.b_qkv, nullptr, 0, 0, SETOK_ACT_NONE, R, 3 * C, C, nullptr, 0};
+  g1.ln_in = rec[0]; g1.ln_s = L.s_qkv; g1.ln_eps = eps; g1.ln_C = C;
+  SETOK_TRY(launch_gemm(g1, stream));
+  SETOK_TRY(launch_attention(qkv, ao, R, C, heads, scale, nullptr, nullptr, T, nullptr, stream));
+  GemmArgs g2{ao, C, L.w_o, C, x, C, SETOK_F32, L.b_o, x, C, SETOK_F32, SETOK_ACT_NONE, R, C, C, nullptr, 0};
+  g2.ln_in = rec[0]; g2.ln_out = rec[1]; g2.xhat = h; g2.ld_xhat = C; g2.ln_eps = eps; g2.ln_C = C;
+  SETOK_TRY(launch_gemm(g2, stream));
+  GemmArgs g3{h, C, L.w_fc1, C, u, F, SETOK_BF16, L.b_fc1, nullptr, 0, 0, act, R, F, C, nullptr, 0};
+  g3.ln_in = rec[1]; g3.ln_s = L.s_fc1; g3.ln_eps = eps; g3.ln_C = C;
+  SETOK_TRY(launch_gemm(g3, stream));
+  GemmArgs g4{u, F, L.w_fc2, F, x, C, SETOK_F32, L.b_fc2, x, C, SETOK_F32, SETOK_ACT_NONE, R, C, F, nullptr, 0};
+  if (emit_next) { g4.ln_in = rec[1]; g4.ln_out = rec[0]; g4.xhat = h; g4.ld_xhat = C; g4.ln_eps = eps; g4.ln_C = C; }
+  SETOK_TRY(launch_gemm(g4, stream));
   return SETOK_OK;
 }
 
@@ -165,11 +197,19 @@ int vit_forward_impl(const setok_vit* v, const void* images, int image_dtype, in
   const int xdt = (v->flags & SETOK_VIT_RESIDUAL_F32) ? SETOK_F32 : SETOK_BF16;
   SETOK_TRY(launch_layernorm(w.emb, SETOK_F32, w.x, xdt, v->pre_ln_g, v->pre_ln_b, v->ln_eps, R, C, nullptr, nullptr, stream));
 
+  const bool fold = (v->flags & SETOK_VIT_LN_FOLD) != 0;
+  if (fold && n_layers_run > 0) SETOK_TRY(launch_ln_fold_init(static_cast<const float*>(w.x), w.h, w.rec[0], v->ln_eps, R, C, stream));
   for (int l = 0; l < n_layers_run; ++l) {
     const setok_vit_layer& L = v->layer[l];
-    SETOK_REQUIRE(L.w_qkv && L.b_qkv && L.w_o && L.b_o && L.w_fc1 && L.b_fc1 && L.w_fc2 && L.b_fc2 && L.ln1_g && L.ln1_b && L.ln2_g && L.ln2_b,
-                  SETOK_ERR_BAD_ARG, "vit_forward: null weights in layer %d", l);
-    SETOK_TRY(run_preln_layer(L, w.x, xdt, w.h, w.qkv, w.ao, w.u, R, T, C, F, v->heads, v->ln_eps, SETOK_ACT_QUICK_GELU, stream));
+    SETOK_REQUIRE(L.w_qkv && L.b_qkv && L.w_o && L.b_o && L.w_fc1 && L.b_fc1 && L.w_fc2 && L.b_fc2, SETOK_ERR_BAD_ARG, "vit_forward: null weights in layer %d", l);
+    if (fold) {
+      SETOK_REQUIRE(L.s_qkv && L.s_fc1, SETOK_ERR_BAD_ARG, "vit_forward: SETOK_VIT_LN_FOLD without s_qkv / s_fc1 in layer %d", l);
+      SETOK_TRY(run_preln_layer_fold(L, static_cast<float*>(w.x), w.h, w.qkv, w.ao, w.u, w.rec, R, T, C, F, v->heads, v->ln_eps, SETOK_ACT_QUICK_GELU,
+                                     l + 1 < n_layers_run, stream));
+    } else {
+      SETOK_REQUIRE(L.ln1_g && L.ln1_b && L.ln2_g && L.ln2_b, SETOK_ERR_BAD_ARG, "vit_forward: null LayerNorm weights in layer %d", l);
+      SETOK_TRY(run_preln_layer(L, w.x, xdt, w.h, w.qkv, w.ao, w.u, R, T, C, F, v->heads, v->ln_eps, SETOK_ACT_QUICK_GELU, stream));
+    }
   }
   // feature_select (clip_encoder.py:40-48)
   SETOK_TRY(launch_select_rows(w.x, xdt, features, feature_dtype, B, T, keep_cls ? 0 : 1, C, pos_add, stream));

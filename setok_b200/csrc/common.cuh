@@ -438,6 +438,16 @@ struct GemmArgs {
   int64_t a_batch_stride = 0, w_batch_stride = 0, d_batch_stride = 0, r_batch_stride = 0;
   // W given as [K, N] row-major (N contiguous) instead of [N, K]: the MN-major B operand form (e.g. V in P.V)
   int w_mn_major = 0;
+  // LayerNorm folded into the GEMMs around it (SETOK_VIT_LN_FOLD; see the epilogue comment in gemm_tcgen05.cu).  Per-row
+  // records of 2 + 2*ns floats, ns = ceil(C / 128): {c, r, (s1, s2) x ns}.
+  //   consumer (ln_in && ln_s):  D = act(a_row * (A W'^T) + b_row * ln_s + bias), A = xhat, W' = gamma (.) W, bias = W beta + b
+  //   producer (ln_in && ln_out && xhat): D = x_new = acc + bias + residual as usual, plus xhat = bf16((x_new - c) * r) and the
+  //                                      row's partial sums of (x_new - c), (x_new - c)^2 over this warp's 128 columns
+  const float* ln_in = nullptr;
+  float* ln_out = nullptr;
+  const float* ln_s = nullptr;
+  void* xhat = nullptr; int64_t ld_xhat = 0;
+  float ln_eps = 0.f; int ln_C = 0;
 };
 int launch_gemm(const GemmArgs& g, cudaStream_t stream);
 extern int g_pdl;   // 1: launch the tower's kernels with programmatic stream serialization (setok_debug_set_pdl)

@@ -50,6 +50,6 @@ int ensure_dynamic_smem(const void* kernel, int bytes) {
 }  // namespace setok
 
 extern "C" const char* setok_last_error(void) { return setok::t_error; }
-extern "C" int setok_abi_version(void) { return 2; }
+extern "C" int setok_abi_version(void) { return 3; }
 extern "C" uint64_t setok_launch_count(void) { return setok::g_launches.load(std::memory_order_relaxed); }
 extern "C" void setok_debug_set_pdl(int on) { setok::g_pdl = on; }

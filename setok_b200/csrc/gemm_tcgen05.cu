@@ -54,6 +54,9 @@ struct GemmDev {
   long long r_batch_stride;   // elements of the residual's type
   int w_mn_major;
   int direct;                 // row-owner epilogue without the shared-memory transpose (see the epilogue branch)
+  const float* ln_in; float* ln_out; const float* ln_s;   // LayerNorm fold (LNF != 0): row records in / out, column sums of W'
+  bf16* xhat; long long ld_xhat;
+  float ln_eps, ln_invC; int ln_ns;
   int epi_mode;               // debug (setok_debug_set_gemm_epi_mode): 0 normal; 1 drain only (no transpose / math / stores);
                               // 2 transpose + math, no residual loads / stores; 3 normal minus the residual loads; 4 / 5: drain only and the
                               // producer stages A only / nothing (is the main loop bound by L2->SM operand traffic?)
@@ -61,7 +64,17 @@ struct GemmDev {
 
 // Epilogue configuration is a template so the per-element code has no run-time branches; -1 = run time
 // (the generic instantiation serves the rarely used combinations).
-template <int CG, int ACT, int RES, int OUTF32, int REMAP, bool DIRECT>
+//
+// LNF (row-owner epilogue only): the pre-LN transformer's LayerNorms folded into the GEMMs on either side of them, so that the
+// residual stream is never re-read by a normalisation pass.  The GEMM that PRODUCES the stream (out_proj / fc2, LNF = 2) also
+// writes xhat = bf16((x - c) * r) -- x normalised with the row's statistics of one sub-layer earlier, (c, r), which are known
+// before the row is complete and keep xhat O(1) so that its bf16 rounding is the rounding the LayerNorm output would get --
+// and, per 128-column half tile, the partial sums s1 = sum(x - c), s2 = sum((x - c)^2).  The GEMM that CONSUMES the normalised
+// rows (qkv / fc1, LNF = 1) multiplies xhat by W' = gamma (.) W and finishes the LayerNorm exactly in its fp32 epilogue:
+//   m = s1 / C, var = s2 / C - m^2, rho = rsqrt(var + eps):  LN(x) = (rho / r) * xhat + rho * (c - mu),  mu = c + m
+//   y_n = (rho / r) * acc_n - rho * m * sum_k W'_nk + (W beta + b)_n
+// The partial sums are added in slot order by every reader: bit-deterministic, no atomics.
+template <int CG, int ACT, int RES, int OUTF32, int REMAP, bool DIRECT, int LNF = 0>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmDev p) {
   constexpr int STAGES = Cfg<CG>::STAGES, B_STAGE_BYTES = Cfg<CG>::B_STAGE_BYTES, STAGE_BYTES = Cfg<CG>::STAGE_BYTES;
@@ -202,6 +215,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
   } else {
     static_assert(!DIRECT || (ACT >= 0 && RES >= 0 && OUTF32 >= 0 && REMAP == 0), "row-owner epilogue: specialised instantiations only");
+    static_assert(LNF != 1 || DIRECT, "LayerNorm fold, consuming side: row-owner epilogue only");
+    static_assert(LNF != 1 || (RES == 0 && OUTF32 == 0), "LayerNorm fold, consuming side: bf16 output, no residual");
+    static_assert(LNF != 2 || (RES == 2 && OUTF32 == 1 && ACT == 0), "LayerNorm fold, producing side: f32 residual stream");
     const int act = ACT >= 0 ? ACT : p.act;
     const int res_kind = RES >= 0 ? RES : p.res_kind;
     const bool out_f32 = OUTF32 >= 0 ? (OUTF32 != 0) : (p.out_f32 != 0);
@@ -248,6 +264,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
         };
         if (RES != 0 && p.epi_mode == 0) { load_res(0, 0); load_res(1, 1); }
+        // LayerNorm fold: this row's record (read under the MMAs of the tile): the consuming side finishes the LayerNorm as
+        // y = ln_a * acc + ln_b * s_n + t_n, the producing side emits xhat = (x - ln_c) * ln_r and its partial sums
+        float ln_a = 1.f, ln_b = 0.f, ln_c = 0.f, ln_r = 1.f, ln_s1 = 0.f, ln_s2 = 0.f;
+        if constexpr (LNF != 0) {
+          if (row_ok) {
+            const float2* rec = reinterpret_cast<const float2*>(p.ln_in + static_cast<long long>(grow) * (2 + 2 * p.ln_ns));
+            const float2 pre = rec[0];
+            float S1 = 0.f, S2 = 0.f;
+            for (int i = 0; i < p.ln_ns; ++i) { const float2 part = rec[1 + i]; S1 += part.x; S2 += part.y; }
+            const float m = S1 * p.ln_invC;
+            const float var = fmaxf(fmaf(-m, m, S2 * p.ln_invC), 0.f);
+            const float rho = rsqrtf(var + p.ln_eps);
+            if (LNF == 1) { ln_a = rho / pre.y; ln_b = -rho * m; }
+            else { ln_c = pre.x + m; ln_r = rho; }
+          }
+        }
+        char* xptr = nullptr;
+        if (LNF == 2) xptr = reinterpret_cast<char*>(p.xhat) + (static_cast<long long>(grow) * p.ld_xhat + n0) * 2;
         mbar_wait(tfull_bar(acc), acc_phase);
         tcgen05_fence_after();
         // accumulator chunks: double-buffered (the next tcgen05.ld in flight under this chunk's math and stores) unless the
@@ -266,12 +300,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             continue;
           }
           uint32_t* outw = a;           // results replace the accumulator words in place (word 2c / 4c is consumed before it is rewritten)
+          uint32_t xw[LNF == 2 ? 8 : 1];
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(bias + gcol0) + c);
-            float v[4] = {__uint_as_float(a[4 * c]) + b4.x, __uint_as_float(a[4 * c + 1]) + b4.y,
-                          __uint_as_float(a[4 * c + 2]) + b4.z, __uint_as_float(a[4 * c + 3]) + b4.w};
+            float v[4];
+            if constexpr (LNF == 1) {
+              const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.ln_s + gcol0) + c);
+              v[0] = fmaf(__uint_as_float(a[4 * c]), ln_a, fmaf(ln_b, s4.x, b4.x));
+              v[1] = fmaf(__uint_as_float(a[4 * c + 1]), ln_a, fmaf(ln_b, s4.y, b4.y));
+              v[2] = fmaf(__uint_as_float(a[4 * c + 2]), ln_a, fmaf(ln_b, s4.z, b4.z));
+              v[3] = fmaf(__uint_as_float(a[4 * c + 3]), ln_a, fmaf(ln_b, s4.w, b4.w));
+            } else {
+              v[0] = __uint_as_float(a[4 * c]) + b4.x; v[1] = __uint_as_float(a[4 * c + 1]) + b4.y;
+              v[2] = __uint_as_float(a[4 * c + 2]) + b4.z; v[3] = __uint_as_float(a[4 * c + 3]) + b4.w;
+            }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               if (ACT == SETOK_ACT_QUICK_GELU) v[e] = act_quick_gelu(v[e]);
@@ -291,6 +335,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
               outw[2 * c] = pack_bf16x2(v[0], v[1]);
               outw[2 * c + 1] = pack_bf16x2(v[2], v[3]);
             }
+            if constexpr (LNF == 2) {
+              float d[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { d[e] = v[e] - ln_c; ln_s1 += d[e]; ln_s2 = fmaf(d[e], d[e], ln_s2); }
+              xw[2 * (c & 3)] = pack_bf16x2(d[0] * ln_r, d[1] * ln_r);
+              xw[2 * (c & 3) + 1] = pack_bf16x2(d[2] * ln_r, d[3] * ln_r);
+              if ((c & 3) == 3 && row_ok) st_global_v8(xptr + ch * 64 + (c >> 2) * 32, xw);     // 16 bf16 = one 32-byte sector
+            }
           }
           if (RES != 0 && ch + 2 < 4 && p.epi_mode == 0) load_res(ch + 2, ch & 1);
           if (row_ok && p.epi_mode != 2) {
@@ -299,12 +351,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
           if (NB == 1 && ch + 1 < 4) tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, ra[0]);
         }
+        if constexpr (LNF == 2) {
+          if (row_ok && n0 < p.N) {
+            float2* rec = reinterpret_cast<float2*>(p.ln_out + static_cast<long long>(grow) * (2 + 2 * p.ln_ns));
+            rec[1 + (n0 >> 7)] = make_float2(ln_s1, ln_s2);
+            if (n0 == 0) rec[0] = make_float2(ln_c, ln_r);
+          }
+        }
         waited = true;
       } else {
       // Residual of the ViT's out_proj / fc2 (x += ...): requested ahead of its use so that the HBM latency overlaps the
       // MMAs instead of being paid once per 32-column chunk.  bf16: the whole tile (4 chunks, 64 registers) before waiting
       // for the accumulator; f32: a ring of two chunks (64 registers), chunk c + 2 requested when chunk c has been consumed.
-      constexpr int PF = (REMAP == 0 && RES == 1) ? 4 : ((REMAP == 0 && RES == 2) ? 2 : 0);
+      // (one chunk ahead only under the LayerNorm fold, whose row-owner pass needs the registers)
+      constexpr int PF = (REMAP == 0 && RES == 1) ? 4 : ((REMAP == 0 && RES == 2) ? (LNF == 2 ? 1 : 2) : 0);
       uint2 rt[PF > 0 && RES == 1 ? PF : 1][8];
       float4 rtf[PF > 0 && RES == 2 ? PF : 1][8];
       auto prefetch = [&](int ch, int slot) {
@@ -326,6 +386,25 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       if (PF > 0 && epi_mode == 0) {
 #pragma unroll
         for (int ch = 0; ch < PF; ++ch) prefetch(ch, ch);
+      }
+      // LayerNorm fold, producing side (HBM-bound shapes keep this epilogue's 128-byte row segments for the f32 stream): the
+      // finished chunk goes back into the warp's staging tile and the thread that owns the row takes its sums and xhat from there
+      float ln_c = 0.f, ln_r = 1.f, ln_s1 = 0.f, ln_s2 = 0.f;
+      const int own_row = row0 + lane;
+      const bool own_ok = own_row < M_eff;
+      char* xptr = nullptr;
+      if constexpr (LNF == 2) {
+        if (own_ok) {
+          const float2* rec = reinterpret_cast<const float2*>(p.ln_in + static_cast<long long>(own_row) * (2 + 2 * p.ln_ns));
+          const float2 pre = rec[0];
+          float S1 = 0.f, S2 = 0.f;
+          for (int i = 0; i < p.ln_ns; ++i) { const float2 part = rec[1 + i]; S1 += part.x; S2 += part.y; }
+          const float m = S1 * p.ln_invC;
+          const float var = fmaxf(fmaf(-m, m, S2 * p.ln_invC), 0.f);
+          ln_c = pre.x + m;
+          ln_r = rsqrtf(var + p.ln_eps);
+        }
+        xptr = reinterpret_cast<char*>(p.xhat) + (static_cast<long long>(own_row) * p.ld_xhat + n0) * 2;
       }
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
@@ -396,6 +475,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             v.x += rf[it].x; v.y += rf[it].y; v.z += rf[it].z; v.w += rf[it].w;
           }
           if (epi_mode == 2) { if (v.x == 1.2345e30f) p.act = 0; continue; }   // keep the math alive, store nothing
+          if constexpr (LNF == 2) *reinterpret_cast<float4*>(stg + r * 128 + ((j ^ (r & 7)) << 4)) = v;
           if (grow < M_eff && col_ok) {
             const long long orow = remap_P > 0 ? (grow + grow / remap_P + 1) : grow;
             if (out_f32) {
@@ -407,6 +487,27 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
         }
         __syncwarp();
+        if constexpr (LNF == 2) {
+          uint32_t xw[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 t = *reinterpret_cast<const float4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4));
+            const float d[4] = {t.x - ln_c, t.y - ln_c, t.z - ln_c, t.w - ln_c};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { ln_s1 += d[e]; ln_s2 = fmaf(d[e], d[e], ln_s2); }
+            xw[2 * (c & 3)] = pack_bf16x2(d[0] * ln_r, d[1] * ln_r);
+            xw[2 * (c & 3) + 1] = pack_bf16x2(d[2] * ln_r, d[3] * ln_r);
+            if ((c & 3) == 3 && own_ok) st_global_v8(xptr + ch * 64 + (c >> 2) * 32, xw);
+          }
+          __syncwarp();
+        }
+      }
+      if constexpr (LNF == 2) {
+        if (own_ok && n0 < p.N) {
+          float2* rec = reinterpret_cast<float2*>(p.ln_out + static_cast<long long>(own_row) * (2 + 2 * p.ln_ns));
+          rec[1 + (n0 >> 7)] = make_float2(ln_s1, ln_s2);
+          if (n0 == 0) rec[0] = make_float2(ln_c, ln_r);
+        }
       }
       }   // transposing epilogue
       if (!waited) { mbar_wait(tfull_bar(acc), acc_phase); tcgen05_fence_after(); }
@@ -522,6 +623,25 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   } else if (g.act == SETOK_ACT_NONE && res_kind == 2 && out_f32) {
     fn = SETOK_PICK(0, 2, 1, 1);                                                                         // patch embedding
   }
+  const int lnf = g.ln_in ? (g.ln_out ? 2 : 1) : 0;
+  if (lnf != 0) {
+    bool ok = g.N % 32 == 0 && g.batch == 1 && g.remap_P == 0 && g.ln_C > 0 && aligned16(g.ln_in);
+    const int de = out_f32 ? 4 : 2;
+    ok = ok && (g.ldd * de) % 32 == 0 && (reinterpret_cast<uintptr_t>(g.D) % 32) == 0;
+    if (lnf == 1) ok = ok && g.ln_s && aligned16(g.ln_s) && res_kind == 0 && !out_f32 && (g.act == SETOK_ACT_NONE || g.act == SETOK_ACT_QUICK_GELU);
+    else ok = ok && g.xhat && res_kind == 2 && out_f32 && g.act == SETOK_ACT_NONE && g.N == g.ln_C && (g.ld_xhat * 2) % 32 == 0 &&
+              (reinterpret_cast<uintptr_t>(g.xhat) % 32) == 0 && (g.ldr * 4) % 32 == 0 && (reinterpret_cast<uintptr_t>(g.residual) % 32) == 0 &&
+              aligned16(g.ln_out) && g.ln_out != g.ln_in;
+    SETOK_REQUIRE(ok, SETOK_ERR_UNSUPPORTED, "gemm: LayerNorm fold (%s side) unsupported for this shape / layout (N=%d C=%d act=%d)",
+                  lnf == 1 ? "consuming" : "producing", g.N, g.ln_C, g.act);
+    // producing side: the automatic choice of the epilogue follows the plain f32-stream GEMMs (transposing at K = 1024, row-owner at K = 4096)
+    direct = lnf == 1 || (g_gemm_epi_direct >= 0 ? g_gemm_epi_direct == 1 : g.K >= 2048);
+#define SETOK_PICK_LN(A, R, O, F) (cg == 2 ? gemm_bf16_tcgen05_kernel<2, A, R, O, 0, true, F> : gemm_bf16_tcgen05_kernel<1, A, R, O, 0, true, F>)
+    if (lnf == 2) fn = direct ? SETOK_PICK_LN(0, 2, 1, 2) : (cg == 2 ? gemm_bf16_tcgen05_kernel<2, 0, 2, 1, 0, false, 2> : gemm_bf16_tcgen05_kernel<1, 0, 2, 1, 0, false, 2>);
+    else if (g.act == SETOK_ACT_QUICK_GELU) fn = SETOK_PICK_LN(1, 0, 0, 1);
+    else fn = SETOK_PICK_LN(0, 0, 0, 1);
+#undef SETOK_PICK_LN
+  }
 #undef SETOK_PICK_D
 #undef SETOK_PICK
   const int smem_bytes = cg == 2 ? Cfg<2>::SMEM_BYTES : Cfg<1>::SMEM_BYTES;
@@ -540,6 +660,8 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   p.batch = g.batch; p.d_batch_stride = g.d_batch_stride; p.r_batch_stride = g.r_batch_stride; p.w_mn_major = g.w_mn_major;
   p.epi_mode = g_gemm_epi_mode;
   p.direct = direct ? 1 : 0;
+  p.ln_in = g.ln_in; p.ln_out = g.ln_out; p.ln_s = g.ln_s; p.xhat = static_cast<bf16*>(g.xhat); p.ld_xhat = g.ld_xhat;
+  p.ln_eps = g.ln_eps; p.ln_invC = g.ln_C > 0 ? 1.0f / static_cast<float>(g.ln_C) : 0.f; p.ln_ns = ceil_div(g.ln_C > 0 ? g.ln_C : 1, 128);
   const int tiles = ceil_div(g.M, BM * cg) * ceil_div(g.N, BN) * g.batch;
   const int max_groups = num_sms() / cg;
   const int grid = (tiles < max_groups ? tiles : max_groups) * cg;

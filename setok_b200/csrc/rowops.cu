@@ -106,6 +106,39 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const TI* __restrict__ i
   }
 }
 
+// ---- LayerNorm fold, first record (SETOK_VIT_LN_FOLD): xhat = bf16((x - mu) * rho) with the row's exact statistics, record
+// {c = mu, r = rho, (s1, s2) = (0, C var), 0 ...}: the consuming GEMM's epilogue then finishes LN(x) = (rho' / rho) * xhat ----
+__global__ void __launch_bounds__(256) ln_fold_init_kernel(const float* __restrict__ in, bf16* __restrict__ xhat, float* __restrict__ rec,
+                                                           float eps, int rows, int C, int ns) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int nvec = C >> 2;
+  const float invC = 1.0f / static_cast<float>(C);
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
+    const float* x = in + static_cast<long long>(r) * C;
+    float s = 0.f;
+    for (int vi = lane; vi < nvec; vi += 32) { const float4 t = Vec4<float>::load(x + vi * 4); s += (t.x + t.y) + (t.z + t.w); }
+    const float mean = warp_sum(s) * invC;
+    float q = 0.f;
+    for (int vi = lane; vi < nvec; vi += 32) {
+      const float4 t = Vec4<float>::load(x + vi * 4);
+      const float a = t.x - mean, b = t.y - mean, c = t.z - mean, d = t.w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+    q = warp_sum(q);
+    const float rho = rsqrtf(q * invC + eps);
+    bf16* y = xhat + static_cast<long long>(r) * C;
+    for (int vi = lane; vi < nvec; vi += 32) {
+      const float4 t = Vec4<float>::load(x + vi * 4);
+      Vec4<bf16>::store(y + vi * 4, make_float4((t.x - mean) * rho, (t.y - mean) * rho, (t.z - mean) * rho, (t.w - mean) * rho));
+    }
+    float2* o = reinterpret_cast<float2*>(rec + static_cast<long long>(r) * (2 + 2 * ns));
+    for (int i = lane; i <= ns; i += 32) o[i] = i == 0 ? make_float2(mean, rho) : (i == 1 ? make_float2(0.f, q) : make_float2(0.f, 0.f));
+  }
+}
+
 // ---- patch embedding im2col: images [B,3,H,W] -> A [B*P, Kp] bf16, columns (c, ky, kx), zero pad ----
 // split: the row is [hi | lo | hi] (3 * Kp columns) with x = hi + lo (bf16 + bf16): against the weight row
 // [w_hi | w_hi | w_lo] one GEMM with K = 3 Kp evaluates x.w = hi.w_hi + lo.w_hi + hi.w_lo, i.e. the patch embedding to
@@ -376,6 +409,16 @@ int launch_layernorm(const void* in, int in_dtype, void* out, int out_dtype, con
   else if (in_dtype == SETOK_BF16 && out_dtype == SETOK_F32) LN_CASE(bf16, float);
   else return fail(SETOK_ERR_BAD_ARG, "layernorm: bad dtypes %d -> %d", in_dtype, out_dtype);
 #undef LN_CASE
+  SETOK_LAUNCH_CHECK();
+  return SETOK_OK;
+}
+
+int launch_ln_fold_init(const float* x, void* xhat_bf16, float* rec, float eps, int rows, int C, cudaStream_t stream) {
+  SETOK_REQUIRE(C % 4 == 0 && aligned16(x) && aligned16(xhat_bf16) && aligned16(rec), SETOK_ERR_BAD_ARG, "ln_fold_init: C %% 4 / alignment");
+  int grid = ceil_div(rows, 8);
+  const int cap = num_sms() * 8;
+  if (grid > cap) grid = cap;
+  SETOK_CUDA_OK(launch_pdl(ln_fold_init_kernel, dim3(grid), dim3(256), 0, stream, x, static_cast<bf16*>(xhat_bf16), rec, eps, rows, C, ceil_div(C, 128)));
   SETOK_LAUNCH_CHECK();
   return SETOK_OK;
 }

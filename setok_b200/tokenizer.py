@@ -23,6 +23,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, List, Optional, Sequence, Union
 
 import numpy as np
@@ -130,11 +131,14 @@ class CLIPVisionTower(PackedParams, nn.Module):
 
     def __init__(self, vision_tower: Optional[str], unfreeze_mm_vision_tower: Optional[bool] = False,
                  mm_vision_select_feature: Optional[str] = "patch", mm_vision_select_layer: Optional[int] = -2,
-                 delay_load=False, vision_config=None, residual_f32: bool = True):
+                 delay_load=False, vision_config=None, residual_f32: bool = True, ln_fold: Optional[bool] = None):
         super().__init__()
         self.is_loaded = False
         # residual stream of the tower kept in float32 between layers (SETOK_VIT_RESIDUAL_F32); False = bf16 stream
         self.residual_f32 = bool(residual_f32)
+        # LayerNorms folded into the GEMMs around them (SETOK_VIT_LN_FOLD, include/setok_b200.h): on by default with the f32
+        # residual stream when the widths allow it; SETOK_VIT_LN_FOLD=0 in the environment keeps the separate LayerNorm passes
+        self.ln_fold = (os.environ.get("SETOK_VIT_LN_FOLD", "1") != "0") if ln_fold is None else bool(ln_fold)
         self.vision_tower_name = vision_tower
         self.select_layer = mm_vision_select_layer
         self.select_feature = mm_vision_select_feature
@@ -209,24 +213,37 @@ class CLIPVisionTower(PackedParams, nn.Module):
         keep["pre_b"] = _f32(sd[pre + "pre_layrnorm.bias"], dev)
         L = cfg.num_hidden_layers
         layers = (_lib.VitLayer * max(L, 1))()
+        fold = self.ln_fold and self.residual_f32 and Cc % 32 == 0 and cfg.intermediate_size % 32 == 0
         for i in range(L):
             q = f"{pre}encoder.layers.{i}."
             t = {
-                "w_qkv": _bf16(torch.cat([sd[q + f"self_attn.{n}_proj.weight"] for n in "qkv"], 0), dev),
+                "w_qkv": _f32(torch.cat([sd[q + f"self_attn.{n}_proj.weight"] for n in "qkv"], 0), dev),
                 "b_qkv": _f32(torch.cat([sd[q + f"self_attn.{n}_proj.bias"] for n in "qkv"], 0), dev),
                 "w_o": _bf16(sd[q + "self_attn.out_proj.weight"], dev), "b_o": _f32(sd[q + "self_attn.out_proj.bias"], dev),
-                "w_fc1": _bf16(sd[q + "mlp.fc1.weight"], dev), "b_fc1": _f32(sd[q + "mlp.fc1.bias"], dev),
+                "w_fc1": _f32(sd[q + "mlp.fc1.weight"], dev), "b_fc1": _f32(sd[q + "mlp.fc1.bias"], dev),
                 "w_fc2": _bf16(sd[q + "mlp.fc2.weight"], dev), "b_fc2": _f32(sd[q + "mlp.fc2.bias"], dev),
                 "ln1_g": _f32(sd[q + "layer_norm1.weight"], dev), "ln1_b": _f32(sd[q + "layer_norm1.bias"], dev),
                 "ln2_g": _f32(sd[q + "layer_norm2.weight"], dev), "ln2_b": _f32(sd[q + "layer_norm2.bias"], dev),
             }
+            for w_, b_, g_, be_, s_ in (("w_qkv", "b_qkv", "ln1_g", "ln1_b", "s_qkv"), ("w_fc1", "b_fc1", "ln2_g", "ln2_b", "s_fc1")):
+                w32_ = t[w_]
+                if fold:
+                    # LN(x) W^T + b = rho (x - mu) (gamma (.) W)^T + (W beta + b): the GEMM runs on W' = bf16(gamma (.) W), its
+                    # epilogue needs s_n = sum_k W'_nk (of the ROUNDED matrix: the mean correction cancels exactly) and t = W beta + b
+                    wg = (w32_ * t[g_][None, :]).to(torch.bfloat16).contiguous()
+                    t[s_] = wg.float().sum(1).contiguous()
+                    t[b_] = ((w32_ * t[be_][None, :]).sum(1) + t[b_]).contiguous()
+                    t[w_] = wg
+                else:
+                    t[w_] = w32_.to(torch.bfloat16).contiguous()
             for k_, v in t.items():
                 keep[f"l{i}.{k_}"] = v
                 setattr(layers[i], k_, v.data_ptr())
         vit = _lib.Vit(image_size=cfg.image_size, patch=p, hidden=Cc, heads=cfg.num_attention_heads, layers=L,
                        mlp=cfg.intermediate_size, ln_eps=float(cfg.layer_norm_eps), w_patch=wp.data_ptr(),
                        cls=keep["cls"].data_ptr(), pos=keep["pos"].data_ptr(), pre_ln_g=keep["pre_g"].data_ptr(),
-                       pre_ln_b=keep["pre_b"].data_ptr(), layer=layers, flags=(_lib.VIT_RESIDUAL_F32 | _lib.VIT_PATCH_SPLIT) if self.residual_f32 else 0)
+                       pre_ln_b=keep["pre_b"].data_ptr(), layer=layers,
+                       flags=((_lib.VIT_RESIDUAL_F32 | _lib.VIT_PATCH_SPLIT) if self.residual_f32 else 0) | (_lib.VIT_LN_FOLD if fold else 0))
         self._packed = (vit, layers, keep)
         self._resized = {}
         return self._packed
@@ -413,7 +430,8 @@ class SetokTokenizer(PackedParams, nn.Module):
                                                      mm_vision_select_feature=mm_vision_select_feature,
                                                      mm_vision_select_layer=mm_vision_select_layer, delay_load=delay_load,
                                                      vision_config=kwargs.get("vision_config"),
-                                                     residual_f32=kwargs.get("tower_residual_f32", True))
+                                                     residual_f32=kwargs.get("tower_residual_f32", True),
+                                                     ln_fold=kwargs.get("tower_ln_fold"))
         self.image_processor = self.image_feature_encoder.image_processor
         self.eval()
 

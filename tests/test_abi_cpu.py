@@ -30,7 +30,7 @@ def test_header_symbols_exported(lib):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/setok_b200.h but not exported"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature in setok_b200/_lib.py"
-    assert lib.setok_abi_version() == 2
+    assert lib.setok_abi_version() == 3
 
 
 def test_argument_validation_without_gpu(lib):
@@ -50,7 +50,7 @@ def test_argument_validation_without_gpu(lib):
 
 def test_struct_layouts_match_header():
     from setok_b200 import _lib
-    assert C.sizeof(_lib.VitLayer) == 12 * 8
+    assert C.sizeof(_lib.VitLayer) == 14 * 8
     assert C.sizeof(_lib.Attn) == 4 * 8
     assert C.sizeof(_lib.Vit) == 6 * 4 + 4 + 4 + 6 * 8 + 8      # 6 ints, float, pad, 6 pointers, flags + pad
     assert _lib.Vit.flags.offset == 80

@@ -432,6 +432,50 @@ def test_tower_uint8_pixels_equal_the_float_path():
     assert torch.equal(rt_u8.data[:n_tok], rt_f.data[:n_tok])
 
 
+@pytest.mark.parametrize("B", [1, 5])
+def test_tower_layernorm_fold_matches_separate_layernorms(B):
+    """SETOK_VIT_LN_FOLD (LayerNorms folded into the GEMMs around them: xhat + row records from the out_proj / fc2 epilogues,
+    the normalisation finished in the qkv / fc1 epilogues) against the same tower with separate LayerNorm passes and against the
+    fp32 oracle, with non-trivial LayerNorm weights and biases and a stream whose row mean and scale drift from layer to layer.
+    B = 1: 65 rows -> single-CTA tiles; B = 5: 325 rows -> CTA pairs, ragged last tile."""
+    C, L, H, P, IMG = 128, 4, 2, 4, 32
+    cfg = dict(hidden_size=C, intermediate_size=4 * C, num_hidden_layers=L, num_attention_heads=H, image_size=IMG, patch_size=P)
+    torch.manual_seed(21)
+    ref_tok = SetokTokenizer("siglip-synthetic", hidden_dim=C, token_feat_dim=64, min_cluster_num=8, threshold=0.5, dim_feedforward=256,
+                             mm_vision_select_layer=-1, vision_config=cfg, tower_ln_fold=False)
+    g = torch.Generator().manual_seed(22)
+    sd = ref_tok.image_feature_encoder.vision_tower.state_dict()
+    for k in sd:
+        if "layer_norm" in k or "layrnorm" in k:
+            sd[k] = (1.0 + 0.3 * torch.randn(sd[k].shape, generator=g)) if k.endswith("weight") else 0.3 * torch.randn(sd[k].shape, generator=g)
+        elif k.endswith("fc2.bias") or k.endswith("out_proj.bias"):
+            sd[k] = 0.5 * torch.randn(sd[k].shape, generator=g)          # shifts the row means between sub-layers
+        elif k.endswith("fc2.weight") or k.endswith("out_proj.weight"):
+            sd[k] = sd[k] * 4.0                                             # and lets the row scale grow with depth
+    ref_tok.image_feature_encoder.vision_tower.load_state_dict(sd)
+    fold_tok = SetokTokenizer("siglip-synthetic", hidden_dim=C, token_feat_dim=64, min_cluster_num=8, threshold=0.5, dim_feedforward=256,
+                              mm_vision_select_layer=-1, vision_config=cfg, tower_ln_fold=True)
+    fold_tok.image_feature_encoder.vision_tower.load_state_dict(sd)
+    ref_tok, fold_tok = ref_tok.to(DEV), fold_tok.to(DEV)
+    images = torch.randn(B, 3, IMG, IMG, generator=g)
+    tp = {k: v.detach().clone() for k, v in sd.items()}
+    for n_run in (1, 2, 4):
+        ref_tok.image_feature_encoder.select_layer = n_run
+        fold_tok.image_feature_encoder.select_layer = n_run
+        f_ref = ref_tok.image_feature_encoder(images.to(DEV))
+        f_fold = fold_tok.image_feature_encoder(images.to(DEV))
+        vit, _, _ = fold_tok.image_feature_encoder._packed_get()
+        assert vit.flags & 4, "the folded tower did not pack with SETOK_VIT_LN_FOLD"
+        assert not (ref_tok.image_feature_encoder._packed_get()[0].flags & 4)
+        oracle = O.clip_vit_hidden_states(images, tp, patch=P, heads=H, layers=L, n_layers_run=n_run)[n_run][:, 1:]
+        e_ref, e_fold, e_pair = _err(f_ref, oracle), _err(f_fold, oracle), _err(f_fold, f_ref)
+        print(f"[ln-fold] B={B} layers={n_run}: separate vs oracle {e_ref}, folded vs oracle {e_fold}, folded vs separate {e_pair}")
+        assert e_fold[1] < max(1.5 * e_ref[1], 2e-3), (n_run, e_ref, e_fold)
+        assert e_fold[0] < max(2.0 * e_ref[0], 4e-3), (n_run, e_ref, e_fold)
+    # determinism: the partial sums are combined in slot order, so two runs agree bit for bit
+    assert torch.equal(fold_tok.image_feature_encoder(images.to(DEV)), f_fold)
+
+
 # ---------------------------------------------------------------------------------------------------
 # The bench configuration itself (BASELINE configs[1]) and configs[2] at full tower depth
 # ---------------------------------------------------------------------------------------------------

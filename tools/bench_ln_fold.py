@@ -1,0 +1,45 @@
+#!/usr/bin/env python
+"""A/B of SETOK_VIT_LN_FOLD on the BASELINE config-2 tower (256 images, ViT-L/14, 23 layers): the LayerNorms folded into the
+GEMMs around them against the separate LayerNorm passes.  Alternates the two towers so that both see the same power state;
+reports time per 256 images, the difference between the two outputs and per-GEMM times of the folded variants.  GPU only."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import bench
+import setok_b200
+
+
+def main():
+    dev = torch.device("cuda:0")
+    towers = {}
+    for name, fold in (("folded", True), ("separate", False)):
+        torch.manual_seed(0)
+        tok = setok_b200.SetokTokenizer("siglip-synthetic-vit-l-14", vision_config=dict(bench.VIT, image_size=224), tower_ln_fold=fold, **bench.HEAD)
+        towers[name] = tok.to(dev).image_feature_encoder
+    from setok_b200.synth import mondrian_images
+    images = mondrian_images(256, 224, 1234, "cpu").to(dev)
+    out = {k: t(images) for k, t in towers.items()}
+    d = (out["folded"] - out["separate"]).float()
+    print(f"folded vs separate: rel-Frobenius {float(d.norm() / out['separate'].float().norm()):.3e}, "
+          f"max abs / max {float(d.abs().max() / out['separate'].float().abs().max()):.3e}", flush=True)
+    reps = int(os.environ.get("REPS", "8"))
+    for rnd in range(3):
+        for name, t in towers.items():
+            for _ in range(2):
+                t(images)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                t(images)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            print(f"round {rnd} {name:9s}: tower {ms:7.2f} ms per 256 images = {256 / ms * 1e3:7.1f} images/s", flush=True)
+
+
+if __name__ == "__main__":
+    main()
