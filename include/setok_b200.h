@@ -56,6 +56,23 @@ int setok_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void
                     int out_dtype, const float* bias, const void* residual, int64_t ldr, int residual_dtype,
                     int act, int M, int N, int K, const int32_t* m_dev, setok_stream_t stream);
 
+/* The LayerNorm-fold forms of setok_gemm_bf16 (what SETOK_VIT_LN_FOLD runs inside the tower, see the flag below): a pre-LN
+ * transformer's LayerNorm (modeling_clip.py:374,381: layer_norm1 / layer_norm2) is never a pass of its own.
+ *   records       (device) f32 [M, 2 + 2*ns], ns = ceil(ln_C / 128): per row {c, r, (s1, s2) x ns}
+ *   producing side (ln_in, ln_out, xhat non-NULL; f32 residual stream, no activation, N == ln_C): besides
+ *                 D = A W^T + bias + residual it writes xhat [M, ld_xhat] bf16 = (D - c') * r' with (c', r') = the mean and
+ *                 inverse standard deviation of the row BEFORE this update (from ln_in), and into ln_out the pair (c', r')
+ *                 plus, per 128-column slot, s1 = sum(D - c'), s2 = sum((D - c')^2)
+ *   consuming side (ln_in, ln_s non-NULL; bf16 output, act none | quick_gelu): A = xhat, W = bf16(gamma (.) W0),
+ *                 bias = W0 beta + b0, ln_s[n] = sum_k float(W[n, k]);  D = act(LayerNorm(x) W0^T + b0) with the row's exact
+ *                 mean / variance taken from the record (m = sum s1 / C, var = sum s2 / C - m^2)
+ * setok_ln_fold_init writes the first record and xhat of a stream x [rows, C] f32 (exact statistics, c = mean, r = rstd). */
+int setok_gemm_bf16_ln(const void* A, int64_t lda, const void* W, int64_t ldw, void* D, int64_t ldd, int out_dtype,
+                       const float* bias, const void* residual, int64_t ldr, int residual_dtype, int act, int M, int N, int K,
+                       const float* ln_in, float* ln_out, const float* ln_s, void* xhat, int64_t ld_xhat, float ln_eps,
+                       int ln_C, setok_stream_t stream);
+int setok_ln_fold_init(const float* x, void* xhat, float* records, float eps, int rows, int C, setok_stream_t stream);
+
 /* Batched form: `batch` independent products D_b = epilogue(A_b * W_b^T); operand b starts at base + b * stride
  * (strides in elements).  With w_mn_major != 0, W_b is given as [K, N] row-major (N contiguous) instead of [N, K] —
  * the form P.V takes in attention (W = V: keys x head_dim).  Used for the dense masked attention of the cluster

@@ -89,6 +89,9 @@ SIGNATURES = {
     "setok_launch_count": (C.c_uint64, []),
     "setok_gemm_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64,
                                 c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "setok_gemm_bf16_ln": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
+                                   c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_int, c_void_p]),
+    "setok_ln_fold_init": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p]),
     "setok_gemm_bf16_batched": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_int64, c_int,
                                         c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "setok_layernorm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p,

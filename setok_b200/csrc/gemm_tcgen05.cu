@@ -19,6 +19,9 @@
 namespace setok {
 namespace {
 
+#ifndef SETOK_LNF_PF
+#define SETOK_LNF_PF 1      // residual chunks requested ahead in the folded transposing epilogue (2 spills 152 bytes; A/B build knob)
+#endif
 constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16;
 constexpr int EPI_WARPS = 8;                      // two warps per TMEM lane quarter, each owning half of the 256 columns
 constexpr int STG_BYTES_PER_WARP = 32 * 32 * 4;   // 32 rows x 32 fp32 columns
@@ -364,7 +367,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       // MMAs instead of being paid once per 32-column chunk.  bf16: the whole tile (4 chunks, 64 registers) before waiting
       // for the accumulator; f32: a ring of two chunks (64 registers), chunk c + 2 requested when chunk c has been consumed.
       // (one chunk ahead only under the LayerNorm fold, whose row-owner pass needs the registers)
-      constexpr int PF = (REMAP == 0 && RES == 1) ? 4 : ((REMAP == 0 && RES == 2) ? (LNF == 2 ? 1 : 2) : 0);
+      constexpr int PF = (REMAP == 0 && RES == 1) ? 4 : ((REMAP == 0 && RES == 2) ? (LNF == 2 ? SETOK_LNF_PF : 2) : 0);
       uint2 rt[PF > 0 && RES == 1 ? PF : 1][8];
       float4 rtf[PF > 0 && RES == 2 ? PF : 1][8];
       auto prefetch = [&](int ch, int slot) {
@@ -688,6 +691,17 @@ extern "C" int setok_gemm_bf16(const void* A, int64_t lda, const void* W, int64_
                                const float* bias, const void* residual, int64_t ldr, int residual_dtype, int act, int M,
                                int N, int K, const int32_t* m_dev, setok_stream_t stream) {
   setok::GemmArgs g{A, lda, W, ldw, D, ldd, out_dtype, bias, residual, ldr, residual_dtype, act, M, N, K, m_dev, 0};
+  return setok::launch_gemm(g, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int setok_gemm_bf16_ln(const void* A, int64_t lda, const void* W, int64_t ldw, void* D, int64_t ldd, int out_dtype,
+                                  const float* bias, const void* residual, int64_t ldr, int residual_dtype, int act, int M, int N, int K,
+                                  const float* ln_in, float* ln_out, const float* ln_s, void* xhat, int64_t ld_xhat, float ln_eps,
+                                  int ln_C, setok_stream_t stream) {
+  SETOK_REQUIRE(ln_in != nullptr && (ln_s != nullptr) != (ln_out != nullptr), SETOK_ERR_BAD_ARG,
+                "gemm_ln: records plus exactly one of ln_s (consuming side) / ln_out (producing side)");
+  setok::GemmArgs g{A, lda, W, ldw, D, ldd, out_dtype, bias, residual, ldr, residual_dtype, act, M, N, K, nullptr, 0};
+  g.ln_in = ln_in; g.ln_out = ln_out; g.ln_s = ln_s; g.xhat = xhat; g.ld_xhat = ld_xhat; g.ln_eps = ln_eps; g.ln_C = ln_C;
   return setok::launch_gemm(g, static_cast<cudaStream_t>(stream));
 }
 

@@ -563,6 +563,11 @@ int launch_convert_rows(const void* in, int in_dtype, void* out, int out_dtype, 
 
 }  // namespace setok
 
+extern "C" int setok_ln_fold_init(const float* x, void* xhat, float* records, float eps, int rows, int C, setok_stream_t stream) {
+  SETOK_REQUIRE(x && xhat && records && rows > 0 && C > 0, SETOK_ERR_BAD_ARG, "ln_fold_init: null pointer or empty shape");
+  return setok::launch_ln_fold_init(x, xhat, records, eps, rows, C, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int setok_layernorm(const void* in, int in_dtype, void* out, int out_dtype, const float* gamma, const float* beta,
                                float eps, int rows, int C, const int32_t* gather, const int32_t* m_dev, setok_stream_t stream) {
   return setok::launch_layernorm(in, in_dtype, out, out_dtype, gamma, beta, eps, rows, C, gather, m_dev, static_cast<cudaStream_t>(stream));

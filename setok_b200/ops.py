@@ -58,6 +58,43 @@ def workspace(dev: torch.device, nbytes: int, tag: str) -> torch.Tensor:
     return buf
 
 
+def ln_records(rows: int, C: int, dev) -> torch.Tensor:
+    """Row records of the folded LayerNorms (setok_gemm_bf16_ln): (rows, 2 + 2 * ceil(C / 128)) float32."""
+    return torch.empty(rows, 2 + 2 * ((C + 127) // 128), dtype=torch.float32, device=dev)
+
+
+def ln_fold_init(x: torch.Tensor, eps: float = 1e-5):
+    """First record and xhat of a float32 residual stream x (rows, C): returns (xhat bf16, records)."""
+    dev = _dev(x)
+    rows, C_ = x.shape
+    xhat = torch.empty(rows, C_, dtype=torch.bfloat16, device=dev)
+    rec = ln_records(rows, C_, dev)
+    with torch.cuda.device(dev):
+        st = _lib.load().setok_ln_fold_init(x.data_ptr(), xhat.data_ptr(), rec.data_ptr(), float(eps), rows, C_, _stream(dev))
+    check(st, "setok_ln_fold_init")
+    return xhat, rec
+
+
+def gemm_ln(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, rec_in: torch.Tensor, *, ln_C: int, eps: float = 1e-5, act: int = ACT_NONE,
+            ln_s: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, rec_out: Optional[torch.Tensor] = None,
+            xhat: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The LayerNorm-fold GEMMs (include/setok_b200.h: setok_gemm_bf16_ln).  Consuming side: ``ln_s`` given, a = xhat, returns
+    act(LN(x) W0^T + b0) in bf16.  Producing side: ``residual`` (the f32 stream, updated in place when ``out`` is it), ``rec_out`` and
+    ``xhat`` given."""
+    dev = _dev(a, w, bias, rec_in, ln_s, residual, rec_out, xhat, out)
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32 if residual is not None else torch.bfloat16, device=dev)
+    with torch.cuda.device(dev):
+        st = _lib.load().setok_gemm_bf16_ln(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0), _dt(out), _p(bias),
+                                            _p(residual), residual.stride(0) if residual is not None else 0, _dt(residual) if residual is not None else 0,
+                                            act, M, N, K, rec_in.data_ptr(), _p(rec_out), _p(ln_s), _p(xhat), xhat.stride(0) if xhat is not None else 0,
+                                            float(eps), int(ln_C), _stream(dev))
+    check(st, "setok_gemm_bf16_ln")
+    return out
+
+
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, act: int = ACT_NONE,
          residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16,
          m_dev: Optional[torch.Tensor] = None) -> torch.Tensor:

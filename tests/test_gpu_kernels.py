@@ -237,3 +237,77 @@ def test_gemm_batched_and_mn_major(Bt, M, N, K, mn):
     _close(out, ref, 1e-4, f"batched gemm mn={mn}")
     out = ops.gemm_batched(a, w, w_mn_major=mn, out_dtype=torch.bfloat16)
     _close(out, ref, 5e-3, f"batched gemm bf16 mn={mn}")
+
+
+# ---------------------------------------------------------------------------------------------------
+# LayerNorm folded into the GEMMs around it (setok_gemm_bf16_ln, setok_ln_fold_init)
+# ---------------------------------------------------------------------------------------------------
+def _fold_pack(w0, b0, gamma, beta):
+    """What the tower packs under SETOK_VIT_LN_FOLD (include/setok_b200.h): W' = bf16(gamma (.) W0), s = row sums of W', t = W0 beta + b0."""
+    wg = (w0 * gamma[None, :]).to(torch.bfloat16).contiguous()
+    return wg, wg.float().sum(1).contiguous(), ((w0 * beta[None, :]).sum(1) + b0).contiguous()
+
+
+@pytest.mark.parametrize("M,C,N2,K2", [(300, 1024, 3072, 1024), (65, 128, 512, 128), (700, 768, 3072, 3072), (160, 96, 256, 64)])
+@pytest.mark.parametrize("act", [ops.ACT_NONE, ops.ACT_QUICK_GELU])
+def test_gemm_layernorm_fold_chain(M, C, N2, K2, act):
+    """x0 -> init -> consumer (LN(x0) W1^T + b1) ; producer (x1 = x0 + a W2^T + b2, xhat / records of x1) -> consumer on x1, against
+    torch fp32 LayerNorm + matmul on the same bf16-rounded operands.  The stream has a large row mean and per-row scale so that
+    the lagged statistics (c, r) of the producer differ visibly from the final ones; C = 96 leaves the last 128-column slot
+    partial, K2 = 3072 takes the row-owner producer epilogue (K >= 2048), the others the transposing one."""
+    g = torch.Generator(device=DEV).manual_seed(M + C + act)
+    eps = 1e-5
+    x0 = (torch.randn(M, C, device=DEV, generator=g) * (0.5 + torch.rand(M, 1, device=DEV, generator=g) * 3) + torch.randn(M, 1, device=DEV, generator=g) * 2).contiguous()
+    gamma = 1.0 + 0.3 * torch.randn(C, device=DEV, generator=g)
+    beta = 0.3 * torch.randn(C, device=DEV, generator=g)
+    w1 = torch.randn(N2, C, device=DEV, generator=g) * C ** -0.5
+    b1 = 0.1 * torch.randn(N2, device=DEV, generator=g)
+    wg, s1, t1 = _fold_pack(w1, b1, gamma, beta)
+
+    def consumer_ref(x):
+        ln = torch.nn.functional.layer_norm(x, (C,), gamma, beta, eps)
+        y = ln @ w1.t() + b1
+        return y * torch.sigmoid(1.702 * y) if act == ops.ACT_QUICK_GELU else y
+
+    xhat, rec = ops.ln_fold_init(x0, eps)
+    y0 = ops.gemm_ln(xhat, wg, t1, rec, ln_C=C, eps=eps, act=act, ln_s=s1)
+    _close(y0, consumer_ref(x0), 1.2e-2, "consumer after init")
+    # producer: x1 = x0 + a W2^T + b2 (in place), with a shift of the row mean and a change of scale
+    a = torch.randn(M, K2, device=DEV, generator=g).to(torch.bfloat16)
+    w2 = (torch.randn(C, K2, device=DEV, generator=g) * (2.0 * K2 ** -0.5)).to(torch.bfloat16)
+    b2 = 0.5 + 0.5 * torch.randn(C, device=DEV, generator=g)
+    x1_ref = x0 + a.float() @ w2.float().t() + b2
+    x1 = x0.clone()
+    rec1 = ops.ln_records(M, C, DEV)
+    xhat1 = torch.empty(M, C, dtype=torch.bfloat16, device=DEV)
+    ops.gemm_ln(a, w2, b2, rec, ln_C=C, eps=eps, residual=x1, rec_out=rec1, xhat=xhat1, out=x1)
+    _close(x1, x1_ref, 1e-4, "producer stream")
+    # the record reconstructs the row statistics of x1 exactly (fp32) ...
+    c, r = rec1[:, 0], rec1[:, 1]
+    S1, S2 = rec1[:, 2::2].sum(1), rec1[:, 3::2].sum(1)
+    mu = c + S1 / C
+    var = S2 / C - (S1 / C) ** 2
+    assert torch.allclose(mu, x1_ref.mean(1), rtol=1e-4, atol=1e-4)
+    assert torch.allclose(var, x1_ref.var(1, unbiased=False), rtol=2e-3, atol=1e-5)
+    # ... (c, r) are the statistics of the row BEFORE the update, and xhat is (x1 - c) r rounded to bf16
+    assert torch.allclose(c, x0.mean(1), rtol=1e-4, atol=1e-4)
+    assert torch.allclose(r, (x0.var(1, unbiased=False) + eps).rsqrt(), rtol=1e-3)
+    _close(xhat1, (x1_ref - c[:, None]) * r[:, None], 2 ** -8, "xhat")
+    y1 = ops.gemm_ln(xhat1, wg, t1, rec1, ln_C=C, eps=eps, act=act, ln_s=s1)
+    _close(y1, consumer_ref(x1_ref), 1.2e-2, "consumer after producer")
+    # a second producer on top (records ping-pong back), checks the chain c' = c + m
+    x2_ref = x1_ref + a.float() @ w2.float().t() + b2
+    ops.gemm_ln(a, w2, b2, rec1, ln_C=C, eps=eps, residual=x1, rec_out=rec, xhat=xhat, out=x1)
+    _close(x1, x2_ref, 1e-4, "second producer stream")
+    assert torch.allclose(rec[:, 0], x1_ref.mean(1), rtol=1e-4, atol=1e-4)
+    y2 = ops.gemm_ln(xhat, wg, t1, rec, ln_C=C, eps=eps, act=act, ln_s=s1)
+    _close(y2, consumer_ref(x2_ref), 1.2e-2, "consumer after the second producer")
+
+
+def test_gemm_layernorm_fold_rejects_bad_layouts():
+    from setok_b200 import SetokError
+    x = torch.randn(64, 100, device=DEV)                    # C % 32 != 0
+    xhat, rec = ops.ln_fold_init(x)
+    w = torch.randn(64, 104, device=DEV).to(torch.bfloat16)[:, :100]
+    with pytest.raises(SetokError):
+        ops.gemm_ln(xhat, w, torch.zeros(64, device=DEV), rec, ln_C=100, ln_s=None)      # neither side selected
