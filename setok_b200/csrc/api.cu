@@ -195,10 +195,11 @@ int vit_forward_impl(const setok_vit* v, const void* images, int image_dtype, in
   SETOK_TRY(launch_gemm(GemmArgs{w.A, Ke, v->w_patch, Ke, w.emb, C, SETOK_F32, nullptr, v->pos, C, SETOK_F32, SETOK_ACT_NONE, B * P, C, Ke, nullptr, P}, stream));
   SETOK_TRY(launch_cls_rows(w.emb, v->cls, v->pos, B, T, C, stream));
   const int xdt = (v->flags & SETOK_VIT_RESIDUAL_F32) ? SETOK_F32 : SETOK_BF16;
-  SETOK_TRY(launch_layernorm(w.emb, SETOK_F32, w.x, xdt, v->pre_ln_g, v->pre_ln_b, v->ln_eps, R, C, nullptr, nullptr, stream));
-
   const bool fold = (v->flags & SETOK_VIT_LN_FOLD) != 0;
-  if (fold && n_layers_run > 0) SETOK_TRY(launch_ln_fold_init(static_cast<const float*>(w.x), w.h, w.rec[0], v->ln_eps, R, C, stream));
+  if (fold && n_layers_run > 0)   // pre_layrnorm, and the first xhat / row records of the stream it starts, in one pass
+    SETOK_TRY(launch_preln_fold_init(w.emb, static_cast<float*>(w.x), w.h, w.rec[0], v->pre_ln_g, v->pre_ln_b, v->ln_eps, R, C, stream));
+  else
+    SETOK_TRY(launch_layernorm(w.emb, SETOK_F32, w.x, xdt, v->pre_ln_g, v->pre_ln_b, v->ln_eps, R, C, nullptr, nullptr, stream));
   for (int l = 0; l < n_layers_run; ++l) {
     const setok_vit_layer& L = v->layer[l];
     SETOK_REQUIRE(L.w_qkv && L.b_qkv && L.w_o && L.b_o && L.w_fc1 && L.b_fc1 && L.w_fc2 && L.b_fc2, SETOK_ERR_BAD_ARG, "vit_forward: null weights in layer %d", l);

@@ -29,6 +29,8 @@ __device__ __forceinline__ int live_rows(int rows, const int32_t* m_dev) {
   return m < rows ? (m < 0 ? 0 : m) : rows;
 }
 
+int g_im2col_rows = 1;   // 0: the element-wise im2col kernels for every patch size (setok_debug_set_im2col_rows; tests compare the two)
+
 // ---- LayerNorm: one warp per row, row cached in registers when C <= 1024 -----------------------
 constexpr int LN_MAXV = 8;   // float4 vectors per lane held in registers (C <= 1024)
 
@@ -139,6 +141,74 @@ __global__ void __launch_bounds__(256) ln_fold_init_kernel(const float* __restri
   }
 }
 
+// pre_layrnorm and the first fold record in one pass (C <= 1024: the row stays in registers): x = LN(emb) gamma + beta is written
+// as the f32 stream and, from the same registers, its own statistics give xhat and the record -- the stream is not re-read.
+__global__ void __launch_bounds__(256) preln_fold_init_kernel(const float* __restrict__ in, float* __restrict__ xout, bf16* __restrict__ xhat,
+                                                              float* __restrict__ rec, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, float eps, int rows, int C, int ns) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int nvec = C >> 2;
+  const float invC = 1.0f / static_cast<float>(C);
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
+    const float* x = in + static_cast<long long>(r) * C;
+    float4 v[LN_MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) { v[i] = Vec4<float>::load(x + vi * 4); s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
+    }
+    const float mean = warp_sum(s) * invC;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) * invC + eps);        // exactly layernorm_kernel's arithmetic: same stream bits
+    float* xo = xout + static_cast<long long>(r) * C;
+    s = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + vi);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + vi);
+        v[i].x = (v[i].x - mean) * rstd * g.x + b.x; v[i].y = (v[i].y - mean) * rstd * g.y + b.y;
+        v[i].z = (v[i].z - mean) * rstd * g.z + b.z; v[i].w = (v[i].w - mean) * rstd * g.w + b.w;
+        Vec4<float>::store(xo + vi * 4, v[i]);
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      }
+    }
+    const float mean2 = warp_sum(s) * invC;
+    q = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        const float a = v[i].x - mean2, b = v[i].y - mean2, c = v[i].z - mean2, d = v[i].w - mean2;
+        q += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+    q = warp_sum(q);
+    const float rho = rsqrtf(q * invC + eps);
+    bf16* y = xhat + static_cast<long long>(r) * C;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) Vec4<bf16>::store(y + vi * 4, make_float4((v[i].x - mean2) * rho, (v[i].y - mean2) * rho, (v[i].z - mean2) * rho, (v[i].w - mean2) * rho));
+    }
+    float2* o = reinterpret_cast<float2*>(rec + static_cast<long long>(r) * (2 + 2 * ns));
+    for (int i = lane; i <= ns; i += 32) o[i] = i == 0 ? make_float2(mean2, rho) : (i == 1 ? make_float2(0.f, q) : make_float2(0.f, 0.f));
+  }
+}
+
 // ---- patch embedding im2col: images [B,3,H,W] -> A [B*P, Kp] bf16, columns (c, ky, kx), zero pad ----
 // split: the row is [hi | lo | hi] (3 * Kp columns) with x = hi + lo (bf16 + bf16): against the weight row
 // [w_hi | w_hi | w_lo] one GEMM with K = 3 Kp evaluates x.w = hi.w_hi + lo.w_hi + hi.w_lo, i.e. the patch embedding to
@@ -215,6 +285,75 @@ __global__ void __launch_bounds__(256) im2col_u8_kernel(const uint8_t* __restric
       }
     }
     store_patch_pair(A, row, Kp, cp, v[0], v[1], split);
+  }
+}
+
+// Row-segment form for even patch sizes (the towers the path runs: 14, 16): one work item = one patch row of one channel
+// = `patch` contiguous pixels -> `patch` contiguous columns (c, ky, :) of the patch's row of A, so there is no per-element
+// index arithmetic, the source is read in whole segments and consecutive items (ky fastest) write adjacent column runs of the
+// same A row.  Items past the three channels zero the pad columns [K, Kp) in runs of `patch`.  U8: uint8 pixels with the
+// processor's rescale / normalize (as im2col_u8_kernel); values identical to the element-wise kernels.
+template <class TI, bool U8, int PATCH>
+__global__ void __launch_bounds__(256) im2col_rows_kernel(const TI* __restrict__ img, bf16* __restrict__ A, int B, int H, int W,
+                                                          int Kp, int split, const __grid_constant__ setok_u8_norm nrm) {
+  __shared__ float lut[U8 ? 256 : 1];
+  if constexpr (U8) {
+    lut[threadIdx.x] = nrm.lut[threadIdx.x];
+    __syncthreads();
+  }
+  const int gw = W / PATCH, gh = H / PATCH;
+  constexpr int K = 3 * PATCH * PATCH;
+  const int pad_items = (Kp - K + PATCH - 1) / PATCH;
+  const int per_row = 3 * PATCH + pad_items;
+  const long long total = static_cast<long long>(B) * gh * gw * per_row;
+  const long long ldA = split ? 3LL * Kp : Kp;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int it = static_cast<int>(i % per_row);
+    const long long row = i / per_row;
+    bf16* dst = A + row * ldA;
+    if (it >= 3 * PATCH) {                                   // zero pad
+      const int col0 = K + (it - 3 * PATCH) * PATCH;
+#pragma unroll
+      for (int e = 0; e < PATCH; e += 2) {
+        if (col0 + e < Kp) {
+          *reinterpret_cast<uint32_t*>(dst + col0 + e) = 0u;
+          if (split) { *reinterpret_cast<uint32_t*>(dst + Kp + col0 + e) = 0u; *reinterpret_cast<uint32_t*>(dst + 2 * Kp + col0 + e) = 0u; }
+        }
+      }
+      continue;
+    }
+    const int c = it / PATCH, ky = it % PATCH;
+    const int px = static_cast<int>(row % gw);
+    const int py = static_cast<int>((row / gw) % gh);
+    const int b = static_cast<int>(row / (static_cast<long long>(gw) * gh));
+    const TI* src = img + ((static_cast<long long>(b) * 3 + c) * H + (py * PATCH + ky)) * W + px * PATCH;
+    float v[PATCH];
+    if constexpr (U8) {
+#pragma unroll
+      for (int e = 0; e < PATCH; e += 2) {
+        const uchar2 u = *reinterpret_cast<const uchar2*>(src + e);
+        v[e] = __fdiv_rn(__fsub_rn(lut[u.x], nrm.mean[c]), nrm.std[c]);
+        v[e + 1] = __fdiv_rn(__fsub_rn(lut[u.y], nrm.mean[c]), nrm.std[c]);
+      }
+    } else if constexpr (sizeof(TI) == 4) {
+#pragma unroll
+      for (int e = 0; e < PATCH; e += 2) { const float2 f = *reinterpret_cast<const float2*>(src + e); v[e] = f.x; v[e + 1] = f.y; }
+    } else {
+#pragma unroll
+      for (int e = 0; e < PATCH; e += 2) { const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(src + e)); v[e] = f.x; v[e + 1] = f.y; }
+    }
+    const int col0 = c * PATCH * PATCH + ky * PATCH;
+#pragma unroll
+    for (int e = 0; e < PATCH; e += 2) {
+      const uint32_t hi = pack_bf16x2(v[e], v[e + 1]);
+      *reinterpret_cast<uint32_t*>(dst + col0 + e) = hi;
+      if (split) {
+        const float2 hf = unpack_bf16x2(hi);
+        *reinterpret_cast<uint32_t*>(dst + Kp + col0 + e) = pack_bf16x2(v[e] - hf.x, v[e + 1] - hf.y);
+        *reinterpret_cast<uint32_t*>(dst + 2 * Kp + col0 + e) = hi;
+      }
+    }
   }
 }
 
@@ -391,6 +530,21 @@ inline int grid_for(long long work_items, int threads, int max_waves = 8) {
   return static_cast<int>(blocks);
 }
 
+template <class TI, bool U8>
+bool launch_im2col_rows(const TI* img, bf16* A, int B, int H, int W, int patch, int Kp, int split, const setok_u8_norm* nrm_host, cudaStream_t stream) {
+  // pixel pairs are read / written as 2-element vectors: even patch size and image width, 4-byte aligned base
+  if ((patch != 14 && patch != 16) || W % 2 != 0 || (reinterpret_cast<uintptr_t>(img) % 4) != 0) return false;
+  const int pad_items = (Kp - 3 * patch * patch + patch - 1) / patch;
+  const long long total = static_cast<long long>(B) * (H / patch) * (W / patch) * (3 * patch + pad_items);
+  const int grid = grid_for(total, 256, 16);
+  static const setok_u8_norm none{};
+  const setok_u8_norm& nrm = nrm_host ? *nrm_host : none;
+  if (patch == 14) im2col_rows_kernel<TI, U8, 14><<<grid, 256, 0, stream>>>(img, A, B, H, W, Kp, split, nrm);
+  else im2col_rows_kernel<TI, U8, 16><<<grid, 256, 0, stream>>>(img, A, B, H, W, Kp, split, nrm);
+  return true;
+}
+
+
 }  // namespace
 
 int launch_layernorm(const void* in, int in_dtype, void* out, int out_dtype, const float* gamma, const float* beta, float eps,
@@ -423,6 +577,24 @@ int launch_ln_fold_init(const float* x, void* xhat_bf16, float* rec, float eps, 
   return SETOK_OK;
 }
 
+// x = LayerNorm(emb) (f32 -> f32) followed by launch_ln_fold_init(x), as one pass when the row fits the register cache
+int launch_preln_fold_init(const float* emb, float* x, void* xhat_bf16, float* rec, const float* gamma, const float* beta, float eps, int rows,
+                           int C, cudaStream_t stream) {
+  if (C % 4 != 0 || (C >> 2) > LN_MAXV * 32) {
+    SETOK_TRY(launch_layernorm(emb, SETOK_F32, x, SETOK_F32, gamma, beta, eps, rows, C, nullptr, nullptr, stream));
+    return launch_ln_fold_init(x, xhat_bf16, rec, eps, rows, C, stream);
+  }
+  SETOK_REQUIRE(aligned16(emb) && aligned16(x) && aligned16(xhat_bf16) && aligned16(rec) && aligned16(gamma) && aligned16(beta), SETOK_ERR_BAD_ARG,
+                "preln_fold_init: buffers must be 16-byte aligned");
+  int grid = ceil_div(rows, 8);
+  const int cap = num_sms() * 8;
+  if (grid > cap) grid = cap;
+  SETOK_CUDA_OK(launch_pdl(preln_fold_init_kernel, dim3(grid), dim3(256), 0, stream, emb, x, static_cast<bf16*>(xhat_bf16), rec, gamma, beta, eps, rows, C,
+                           ceil_div(C, 128)));
+  SETOK_LAUNCH_CHECK();
+  return SETOK_OK;
+}
+
 int launch_masked_softmax(const float* S, void* P, const int32_t* seg_off, const int32_t* row_seg, int rows, int N, int ldS, int ldP,
                           float scale, cudaStream_t stream) {
   int grid = ceil_div(rows, 8);
@@ -436,6 +608,14 @@ int launch_masked_softmax(const float* S, void* P, const int32_t* seg_off, const
 int launch_im2col(const void* images, int image_dtype, void* A, int B, int H, int W, int patch, int Kp, int split, cudaStream_t stream) {
   const long long total = static_cast<long long>(B) * (H / patch) * (W / patch) * (Kp / 2);
   const int grid = grid_for(total, 256, 16);
+  if (g_im2col_rows && image_dtype == SETOK_F32 && launch_im2col_rows<float, false>(static_cast<const float*>(images), static_cast<bf16*>(A), B, H, W, patch, Kp, split, nullptr, stream)) {
+    SETOK_LAUNCH_CHECK();
+    return SETOK_OK;
+  }
+  if (g_im2col_rows && image_dtype == SETOK_BF16 && launch_im2col_rows<bf16, false>(static_cast<const bf16*>(images), static_cast<bf16*>(A), B, H, W, patch, Kp, split, nullptr, stream)) {
+    SETOK_LAUNCH_CHECK();
+    return SETOK_OK;
+  }
   if (image_dtype == SETOK_F32) im2col_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(images), static_cast<bf16*>(A), B, H, W, patch, Kp, split);
   else if (image_dtype == SETOK_BF16) im2col_kernel<bf16><<<grid, 256, 0, stream>>>(static_cast<const bf16*>(images), static_cast<bf16*>(A), B, H, W, patch, Kp, split);
   else return fail(SETOK_ERR_BAD_ARG, "im2col: bad image dtype %d", image_dtype);
@@ -445,6 +625,10 @@ int launch_im2col(const void* images, int image_dtype, void* A, int B, int H, in
 
 int launch_im2col_u8(const uint8_t* images, const setok_u8_norm* norm, void* A, int B, int H, int W, int patch, int Kp, int split, cudaStream_t stream) {
   const long long total = static_cast<long long>(B) * (H / patch) * (W / patch) * (Kp / 2);
+  if (g_im2col_rows && launch_im2col_rows<uint8_t, true>(images, static_cast<bf16*>(A), B, H, W, patch, Kp, split, norm, stream)) {
+    SETOK_LAUNCH_CHECK();
+    return SETOK_OK;
+  }
   im2col_u8_kernel<<<grid_for(total, 256, 16), 256, 0, stream>>>(images, static_cast<bf16*>(A), B, H, W, patch, Kp, split, *norm);
   SETOK_LAUNCH_CHECK();
   return SETOK_OK;
@@ -562,6 +746,8 @@ int launch_convert_rows(const void* in, int in_dtype, void* out, int out_dtype, 
 }
 
 }  // namespace setok
+
+extern "C" void setok_debug_set_im2col_rows(int on) { setok::g_im2col_rows = on; }
 
 extern "C" int setok_ln_fold_init(const float* x, void* xhat, float* records, float eps, int rows, int C, setok_stream_t stream) {
   SETOK_REQUIRE(x && xhat && records && rows > 0 && C > 0, SETOK_ERR_BAD_ARG, "ln_fold_init: null pointer or empty shape");

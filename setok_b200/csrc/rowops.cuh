@@ -24,5 +24,7 @@ int launch_add_pos_rows(const float* in, const float* pos, void* out_bf16, int r
 int launch_zero_tail_rows(void* buf_bf16, long long ld, const int32_t* n_live_dev, int n_rows, int cap, int cols, cudaStream_t stream);
 // first LayerNorm-fold record of the residual stream x [rows, C] f32 (records of 2 + 2*ceil(C/128) floats) and its xhat
 int launch_ln_fold_init(const float* x, void* xhat_bf16, float* rec, float eps, int rows, int C, cudaStream_t stream);
+int launch_preln_fold_init(const float* emb, float* x, void* xhat_bf16, float* rec, const float* gamma, const float* beta, float eps, int rows,
+                           int C, cudaStream_t stream);
 int get_pos_table(int h, int w, int C, const float** out, cudaStream_t stream);
 }  // namespace setok

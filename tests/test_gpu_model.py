@@ -432,6 +432,32 @@ def test_tower_uint8_pixels_equal_the_float_path():
     assert torch.equal(rt_u8.data[:n_tok], rt_f.data[:n_tok])
 
 
+@pytest.mark.parametrize("P,IMG", [(14, 42), (16, 64)])
+def test_im2col_row_segment_kernels_equal_the_elementwise_ones(P, IMG):
+    """Patch sizes 14 / 16 take the row-segment im2col (one work item per patch row of a channel, float and uint8 forms); the
+    element-wise kernels (any patch size) must give bit-identical tower features."""
+    import ctypes
+    from setok_b200 import _lib
+    C, L, H = 64, 1, 2
+    cfg = dict(hidden_size=C, intermediate_size=4 * C, num_hidden_layers=L, num_attention_heads=H, image_size=IMG, patch_size=P)
+    tok = _make_tokenizer(C, 64, 256, 4, 0.5, cfg, select_layer=-1, seed=13)
+    tower = tok.image_feature_encoder
+    g = torch.Generator().manual_seed(14)
+    u8 = torch.randint(0, 256, (3, 3, IMG, IMG), dtype=torch.uint8, generator=g).to(DEV)
+    f32 = torch.randn(3, 3, IMG, IMG, generator=g).to(DEV)
+    lib = _lib.load()
+    lib.setok_debug_set_im2col_rows.argtypes = [ctypes.c_int]
+    lib.setok_debug_set_im2col_rows.restype = None
+    try:
+        lib.setok_debug_set_im2col_rows(0)
+        ref = [tower(u8).clone(), tower(f32).clone(), tower(f32.to(torch.bfloat16)).clone()]
+    finally:
+        lib.setok_debug_set_im2col_rows(1)
+    got = [tower(u8), tower(f32), tower(f32.to(torch.bfloat16))]
+    for a, b in zip(got, ref):
+        assert torch.isfinite(a.float()).all() and torch.equal(a, b)
+
+
 @pytest.mark.parametrize("B", [1, 5])
 def test_tower_layernorm_fold_matches_separate_layernorms(B):
     """SETOK_VIT_LN_FOLD (LayerNorms folded into the GEMMs around them: xhat + row records from the out_proj / fc2 epilogues,
