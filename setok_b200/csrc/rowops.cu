@@ -288,11 +288,11 @@ __global__ void __launch_bounds__(256) im2col_u8_kernel(const uint8_t* __restric
   }
 }
 
-// Row-segment form for even patch sizes (the towers the path runs: 14, 16): one work item = one patch row of one channel
-// = `patch` contiguous pixels -> `patch` contiguous columns (c, ky, :) of the patch's row of A, so there is no per-element
-// index arithmetic, the source is read in whole segments and consecutive items (ky fastest) write adjacent column runs of the
-// same A row.  Items past the three channels zero the pad columns [K, Kp) in runs of `patch`.  U8: uint8 pixels with the
-// processor's rescale / normalize (as im2col_u8_kernel); values identical to the element-wise kernels.
+// Vector form for the patch sizes the path runs (14, 16; compile-time, so the (c, ky, kx) split of a column index is constant
+// multiplies): one work item = 8 consecutive columns of one patch row of A -> one aligned 16-byte store per segment
+// ([hi | lo | hi] with `split`), a warp writes 512 contiguous bytes per instruction; the 8 pixels come from at most two short
+// runs of the image (L1-resident across neighbouring items).  U8: uint8 pixels with the processor's rescale / normalize (as
+// im2col_u8_kernel).  Values identical to the element-wise kernels.
 template <class TI, bool U8, int PATCH>
 __global__ void __launch_bounds__(256) im2col_rows_kernel(const TI* __restrict__ img, bf16* __restrict__ A, int B, int H, int W,
                                                           int Kp, int split, const __grid_constant__ setok_u8_norm nrm) {
@@ -302,57 +302,42 @@ __global__ void __launch_bounds__(256) im2col_rows_kernel(const TI* __restrict__
     __syncthreads();
   }
   const int gw = W / PATCH, gh = H / PATCH;
-  constexpr int K = 3 * PATCH * PATCH;
-  const int pad_items = (Kp - K + PATCH - 1) / PATCH;
-  const int per_row = 3 * PATCH + pad_items;
+  constexpr int PP = PATCH * PATCH, K = 3 * PP;
+  const int per_row = Kp >> 3;
   const long long total = static_cast<long long>(B) * gh * gw * per_row;
   const long long ldA = split ? 3LL * Kp : Kp;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int it = static_cast<int>(i % per_row);
+    const int j = static_cast<int>(i % per_row);
     const long long row = i / per_row;
-    bf16* dst = A + row * ldA;
-    if (it >= 3 * PATCH) {                                   // zero pad
-      const int col0 = K + (it - 3 * PATCH) * PATCH;
-#pragma unroll
-      for (int e = 0; e < PATCH; e += 2) {
-        if (col0 + e < Kp) {
-          *reinterpret_cast<uint32_t*>(dst + col0 + e) = 0u;
-          if (split) { *reinterpret_cast<uint32_t*>(dst + Kp + col0 + e) = 0u; *reinterpret_cast<uint32_t*>(dst + 2 * Kp + col0 + e) = 0u; }
-        }
-      }
-      continue;
-    }
-    const int c = it / PATCH, ky = it % PATCH;
     const int px = static_cast<int>(row % gw);
     const int py = static_cast<int>((row / gw) % gh);
     const int b = static_cast<int>(row / (static_cast<long long>(gw) * gh));
-    const TI* src = img + ((static_cast<long long>(b) * 3 + c) * H + (py * PATCH + ky)) * W + px * PATCH;
-    float v[PATCH];
-    if constexpr (U8) {
+    const TI* src = img + (static_cast<long long>(b) * 3 * H + py * PATCH) * W + px * PATCH;
+    float v[8];
 #pragma unroll
-      for (int e = 0; e < PATCH; e += 2) {
-        const uchar2 u = *reinterpret_cast<const uchar2*>(src + e);
-        v[e] = __fdiv_rn(__fsub_rn(lut[u.x], nrm.mean[c]), nrm.std[c]);
-        v[e + 1] = __fdiv_rn(__fsub_rn(lut[u.y], nrm.mean[c]), nrm.std[c]);
+    for (int e = 0; e < 8; ++e) {
+      const int col = 8 * j + e;
+      v[e] = 0.f;
+      if (col < K) {
+        const int c = col / PP, rem = col % PP;
+        const int ky = rem / PATCH, kx = rem % PATCH;
+        const TI* q = src + (static_cast<long long>(c) * H + ky) * W + kx;
+        if constexpr (U8) v[e] = __fdiv_rn(__fsub_rn(lut[*q], nrm.mean[c]), nrm.std[c]);
+        else v[e] = to_f32<TI>(*q);
       }
-    } else if constexpr (sizeof(TI) == 4) {
-#pragma unroll
-      for (int e = 0; e < PATCH; e += 2) { const float2 f = *reinterpret_cast<const float2*>(src + e); v[e] = f.x; v[e + 1] = f.y; }
-    } else {
-#pragma unroll
-      for (int e = 0; e < PATCH; e += 2) { const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(src + e)); v[e] = f.x; v[e + 1] = f.y; }
     }
-    const int col0 = c * PATCH * PATCH + ky * PATCH;
-#pragma unroll
-    for (int e = 0; e < PATCH; e += 2) {
-      const uint32_t hi = pack_bf16x2(v[e], v[e + 1]);
-      *reinterpret_cast<uint32_t*>(dst + col0 + e) = hi;
-      if (split) {
-        const float2 hf = unpack_bf16x2(hi);
-        *reinterpret_cast<uint32_t*>(dst + Kp + col0 + e) = pack_bf16x2(v[e] - hf.x, v[e + 1] - hf.y);
-        *reinterpret_cast<uint32_t*>(dst + 2 * Kp + col0 + e) = hi;
-      }
+    uint4 hi;
+    hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]); hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
+    bf16* dst = A + row * ldA + 8 * j;
+    *reinterpret_cast<uint4*>(dst) = hi;
+    if (split) {
+      const float2 h0 = unpack_bf16x2(hi.x), h1 = unpack_bf16x2(hi.y), h2 = unpack_bf16x2(hi.z), h3 = unpack_bf16x2(hi.w);
+      uint4 lo;
+      lo.x = pack_bf16x2(v[0] - h0.x, v[1] - h0.y); lo.y = pack_bf16x2(v[2] - h1.x, v[3] - h1.y);
+      lo.z = pack_bf16x2(v[4] - h2.x, v[5] - h2.y); lo.w = pack_bf16x2(v[6] - h3.x, v[7] - h3.y);
+      *reinterpret_cast<uint4*>(dst + Kp) = lo;
+      *reinterpret_cast<uint4*>(dst + 2 * Kp) = hi;
     }
   }
 }
@@ -532,10 +517,8 @@ inline int grid_for(long long work_items, int threads, int max_waves = 8) {
 
 template <class TI, bool U8>
 bool launch_im2col_rows(const TI* img, bf16* A, int B, int H, int W, int patch, int Kp, int split, const setok_u8_norm* nrm_host, cudaStream_t stream) {
-  // pixel pairs are read / written as 2-element vectors: even patch size and image width, 4-byte aligned base
-  if ((patch != 14 && patch != 16) || W % 2 != 0 || (reinterpret_cast<uintptr_t>(img) % 4) != 0) return false;
-  const int pad_items = (Kp - 3 * patch * patch + patch - 1) / patch;
-  const long long total = static_cast<long long>(B) * (H / patch) * (W / patch) * (3 * patch + pad_items);
+  if ((patch != 14 && patch != 16) || Kp % 8 != 0 || (reinterpret_cast<uintptr_t>(A) % 16) != 0) return false;   // 16-byte stores
+  const long long total = static_cast<long long>(B) * (H / patch) * (W / patch) * (Kp / 8);
   const int grid = grid_for(total, 256, 16);
   static const setok_u8_norm none{};
   const setok_u8_norm& nrm = nrm_host ? *nrm_host : none;

@@ -433,8 +433,8 @@ def test_tower_uint8_pixels_equal_the_float_path():
 
 
 @pytest.mark.parametrize("P,IMG", [(14, 42), (16, 64)])
-def test_im2col_row_segment_kernels_equal_the_elementwise_ones(P, IMG):
-    """Patch sizes 14 / 16 take the row-segment im2col (one work item per patch row of a channel, float and uint8 forms); the
+def test_im2col_vector_kernels_equal_the_elementwise_ones(P, IMG):
+    """Patch sizes 14 / 16 take the vector im2col (8 columns = one 16-byte store per work item; float, bf16 and uint8 forms); the
     element-wise kernels (any patch size) must give bit-identical tower features."""
     import ctypes
     from setok_b200 import _lib

@@ -26,6 +26,13 @@ def main():
     print(f"folded vs separate: rel-Frobenius {float(d.norm() / out['separate'].float().norm()):.3e}, "
           f"max abs / max {float(d.abs().max() / out['separate'].float().abs().max()):.3e}", flush=True)
     reps = int(os.environ.get("REPS", "8"))
+    if os.environ.get("EPI_DIRECT"):      # -1 automatic, 0 / 1: force the transposing / row-owner epilogue where both exist (A/B of the producers)
+        import ctypes
+        from setok_b200 import _lib
+        lib = _lib.load()
+        lib.setok_debug_set_gemm_epi_direct.argtypes = [ctypes.c_int]
+        lib.setok_debug_set_gemm_epi_direct(int(os.environ["EPI_DIRECT"]))
+        print("gemm epilogue override:", os.environ["EPI_DIRECT"])
     for rnd in range(3):
         for name, t in towers.items():
             for _ in range(2):
