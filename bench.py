@@ -45,10 +45,10 @@ DETOK = dict(token_feat_dim=1024, hidden_dim=768, patch_size=14, image_size=336,
 KNN_K = 16
 BATCH = 256
 SEED = 1234
-# dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch, mean of fc2/qkv/out_proj/fc1 with the f32 residual stream
-# (profiles/r02_ncu_summary.md); the algorithmic operand bytes of the same mix are 742e6
-NCU_GEMM_DRAM_BYTES_PER_LAUNCH = (1109.2e6 + 497.3e6 + 623.5e6 + 634.5e6) / 4
-NCU_CLUSTER_DRAM_BYTES_PER_LAUNCH = 268.8e6 + 5.9e6   # dpc_fused_kernel, dram read + write (profiles/r02_ncu_summary.md)
+# dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch, mean of fc2/qkv/out_proj/fc1 with the f32 residual stream and the
+# LayerNorms folded into them (profiles/r02_ncu_summary.md); the algorithmic operand bytes of the same mix are 815e6
+NCU_GEMM_DRAM_BYTES_PER_LAUNCH = (1284.8e6 + 501.9e6 + 765.0e6 + 642.1e6) / 4   # fc2 / qkv / out_proj / fc1, LayerNorm-fold variants (profiles/r02_ncu_summary.md)
+NCU_CLUSTER_DRAM_BYTES_PER_LAUNCH = 268.8e6 + 6.1e6   # dpc_fused_kernel, dram read + write (profiles/r02_ncu_summary.md)
 
 WORKLOADS = {
     2: "BASELINE config 2: batch 256 synthetic 224^2 Mondrian images per GPU, ViT-L/14 (23 of 24 layers, select_layer -2), "
@@ -536,7 +536,7 @@ def run_config2(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic", "config": dict(workload_config(2, world), ragged_all_gather=gather is not None,
-                                            tower_residual_stream="f32", k_per_image={"min": float(counts.min()), "mean": float(counts.mean()), "max": float(counts.max())}),
+                                            tower_residual_stream="f32", tower_layernorm="folded into the qkv / out_proj / fc1 / fc2 GEMM epilogues (SETOK_VIT_LN_FOLD)", k_per_image={"min": float(counts.min()), "mean": float(counts.mean()), "max": float(counts.max())}),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h_u8.numel() + h_noise.numel() * 4, "d2h_bytes_per_step": d2h,
                 "input": "uint8 pixels (B,3,224,224) from pinned host memory; rescale + normalize inside the patch-embedding pass",
                 "float32_input_value": e2e_f32, "float32_input_h2d_bytes_per_step": h_f32.numel() * 4 + h_noise.numel() * 4},
@@ -544,12 +544,14 @@ def run_config2(args):
         "clocks": clocks,
         "roofline": {"kernel": "gemm_bf16_tcgen05_kernel (ViT layer launch mix: qkv/out_proj/fc1/fc2 at M=65792, f32 residual stream, LayerNorms folded into the epilogues)", "bound": "tensor",
                      "achieved": gemm_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": gemm_tf / pk["tf_sustained"],
-                     "traffic": NCU_GEMM_DRAM_BYTES_PER_LAUNCH, "traffic_source": "ncu --set full dram__bytes_read+write, mean over the 4 shapes (profiles/r02_ncu_summary.md); algorithmic operand bytes are 742e6 with the f32 residual stream",
+                     "traffic": NCU_GEMM_DRAM_BYTES_PER_LAUNCH, "traffic_source": "ncu --set full dram__bytes_read+write, mean over the 4 shapes (profiles/r02_ncu_summary.md); algorithmic operand bytes are 815e6 with the f32 residual stream and the xhat / row-record outputs of the folded LayerNorms",
+                     "note": "the launches carry the layers' LayerNorm work (SETOK_VIT_LN_FOLD: xhat + row sums written by out_proj / fc2, normalisation finished in the qkv / fc1 epilogues): "
+                             "per launch they are ~6 % slower than the plain GEMM variants, and the 46 LayerNorm passes per step are gone (tower -3.3 %, tools/bench_ln_fold.py)",
                      "flops_per_launch": gemm_flops, "ms_per_launch": gemm_ms,
                      "peak_source": f"{pk['src']} sustained bf16 (kernel timed inside a long loop)",
                      "step_share": (4 * layers_run * gemm_ms) / step_ms,
                      "vit_tensor_frac_of_step": (BATCH * vit_flops_per_image(layers_run) / (step_ms * 1e-3) / 1e12) / pk["tf_sustained"]},
-        "roofline_vit": {"kernel": "whole ViT-L/14 tower (im2col, patch GEMM, 23 x [LN, qkv, attention, out_proj, LN, fc1, fc2])", "bound": "tensor",
+        "roofline_vit": {"kernel": "whole ViT-L/14 tower (im2col, patch GEMM, pre-LN, 23 x [qkv, attention, out_proj, fc1, fc2] with the LayerNorms folded into the GEMMs)", "bound": "tensor",
                          "achieved": vit_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": vit_tf / pk["tf_sustained"],
                          "ms": vit_ms, "flops": BATCH * vit_flops_per_image(layers_run)},
         "roofline_cluster": {"kernel": "dpc_fused_kernel (a4 on the position-embedded tensor; a3 is fused into the tower's last row pass), B=256 N=256 C=1024 feature-injected", "bound": "hbm",
