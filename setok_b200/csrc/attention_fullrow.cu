@@ -301,7 +301,6 @@ attn_fullrow_hd64_kernel(const __grid_constant__ CUtensorMap tm256, const __grid
     const uint32_t treg = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + 256u * t;
     const float sl2 = p.scale_log2;
     const bool masked = nkeys < 256;
-    const int nchunks = (Nk + 63) >> 6;
     float inv_l = 0.f;
     for (int n = 0; n_local > 0 && n <= n_local; ++n) {
       const int g = static_cast<int>(blockIdx.x) + (n - 1) * static_cast<int>(gridDim.x);     // pair whose O is drained now
@@ -379,66 +378,71 @@ attn_fullrow_hd64_kernel(const __grid_constant__ CUtensorMap tm256, const __grid
       mbar_wait(s_full(t), n & 1);
       FR_TRACE(t, 3);
       tcgen05_fence_after();
+      // Both passes walk the row in 32-key steps with two register buffers: the tcgen05.ld of step h + 1 is issued right after
+      // the wait for step h and flies under step h's arithmetic (tcgen05.wait::ld covers every outstanding load, so the order
+      // is wait -> issue next -> compute), instead of one exposed tensor-memory round trip per 64-key chunk.
+      const int nsteps = (Nk + 31) >> 5;
+      uint32_t ra[32], rb[32];
       // pass 1: row maximum over the keys
       float mx0 = s_x, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < ((p.dbg & 1) ? 0 : nchunks); ++c) {
-        uint32_t r[64];
-        tmem_ld_32x32b_x32(treg + 64 * c, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
-        tmem_ld_32x32b_x32(treg + 64 * c + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
-        tmem_ld_wait();
+      auto max32 = [&](uint32_t (&r)[32], int h) {
         if (masked) {
 #pragma unroll
-          for (int i = 0; i < 64; ++i) if (64 * c + i >= nkeys) r[i] = 0xff800000u;
+          for (int i = 0; i < 32; ++i) if (32 * h + i >= nkeys) r[i] = 0xff800000u;
         }
 #pragma unroll
-        for (int i = 0; i < 64; i += 4) {
+        for (int i = 0; i < 32; i += 4) {
           mx0 = fmaxf(mx0, __uint_as_float(r[i])); mx1 = fmaxf(mx1, __uint_as_float(r[i + 1]));
           mx2 = fmaxf(mx2, __uint_as_float(r[i + 2])); mx3 = fmaxf(mx3, __uint_as_float(r[i + 3]));
+        }
+      };
+      if (!(p.dbg & 1)) {
+        tmem_ld_32x32b_x32(treg, ra);
+#pragma unroll 1
+        for (int h = 0; h < nsteps; h += 2) {
+          tmem_ld_wait();
+          if (h + 1 < nsteps) tmem_ld_32x32b_x32(treg + 32 * (h + 1), rb);
+          max32(ra, h);
+          if (h + 1 < nsteps) {
+            tmem_ld_wait();
+            if (h + 2 < nsteps) tmem_ld_32x32b_x32(treg + 32 * (h + 2), ra);
+            max32(rb, h + 1);
+          }
         }
       }
       FR_TRACE(t, 4);
       const float m = (p.dbg & 1) ? 8.0f : fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sl2;
       const bool no_exp = (p.dbg & 2) != 0;
-      const bool packed_exp = (p.dbg & 16) != 0;
-      // pass 2: p = exp2(s * scale - m); P (bf16 pairs) goes back over the S columns already consumed
+      // pass 2: p = exp2(s * scale - m); P (bf16 pairs) goes back over the S columns already consumed: the 16 columns of step h
+      // lie inside step floor(h / 2)'s score columns, which are in registers or done with by then
       float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < nchunks; ++c) {
-        uint32_t r[64];
-        tmem_ld_32x32b_x32(treg + 64 * c, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
-        tmem_ld_32x32b_x32(treg + 64 * c + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
-        tmem_ld_wait();
+      auto exp32 = [&](uint32_t (&r)[32], int h) {
         if (masked) {
 #pragma unroll
-          for (int i = 0; i < 64; ++i) if (64 * c + i >= nkeys) r[i] = 0xff800000u;
+          for (int i = 0; i < 32; ++i) if (32 * h + i >= nkeys) r[i] = 0xff800000u;
         }
-        if (packed_exp) {
-          // two exponentials per MUFU op: arguments rounded to bf16 pairs, ex2.approx.ftz.bf16x2 returns the P pair itself
 #pragma unroll
-          for (int i = 0; i < 64; i += 4) {
-            const uint32_t xa = pack_bf16x2(fmaf(__uint_as_float(r[i]), sl2, -m), fmaf(__uint_as_float(r[i + 1]), sl2, -m));
-            const uint32_t xb = pack_bf16x2(fmaf(__uint_as_float(r[i + 2]), sl2, -m), fmaf(__uint_as_float(r[i + 3]), sl2, -m));
-            uint32_t pa, pb;
-            asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(pa) : "r"(xa));
-            asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(pb) : "r"(xb));
-            ps0 += __uint_as_float(pa << 16); ps1 += __uint_as_float(pa & 0xffff0000u);
-            ps2 += __uint_as_float(pb << 16); ps3 += __uint_as_float(pb & 0xffff0000u);
-            r[i / 2] = pa;
-            r[i / 2 + 1] = pb;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 64; i += 4) {
-            float p0 = fmaf(__uint_as_float(r[i]), sl2, -m), p1 = fmaf(__uint_as_float(r[i + 1]), sl2, -m);
-            float p2 = fmaf(__uint_as_float(r[i + 2]), sl2, -m), p3 = fmaf(__uint_as_float(r[i + 3]), sl2, -m);
-            if (!no_exp) { p0 = fr_exp2(p0); p1 = fr_exp2(p1); p2 = fr_exp2(p2); p3 = fr_exp2(p3); }
-            ps0 += p0; ps1 += p1; ps2 += p2; ps3 += p3;
-            r[i / 2] = pack_bf16x2(p0, p1);               // in place: slots <= i/2+1 were consumed already
-            r[i / 2 + 1] = pack_bf16x2(p2, p3);
-          }
+        for (int i = 0; i < 32; i += 4) {
+          float p0 = fmaf(__uint_as_float(r[i]), sl2, -m), p1 = fmaf(__uint_as_float(r[i + 1]), sl2, -m);
+          float p2 = fmaf(__uint_as_float(r[i + 2]), sl2, -m), p3 = fmaf(__uint_as_float(r[i + 3]), sl2, -m);
+          if (!no_exp) { p0 = fr_exp2(p0); p1 = fr_exp2(p1); p2 = fr_exp2(p2); p3 = fr_exp2(p3); }
+          ps0 += p0; ps1 += p1; ps2 += p2; ps3 += p3;
+          r[i / 2] = pack_bf16x2(p0, p1);               // in place: slots <= i/2+1 were consumed already
+          r[i / 2 + 1] = pack_bf16x2(p2, p3);
         }
-        if (!(p.dbg & 4)) tmem_st_32x32b_x32(treg + 32 * c, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+        if (!(p.dbg & 4)) tmem_st_32x32b_x16(treg + 16 * h, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+      };
+      tmem_ld_32x32b_x32(treg, ra);
+#pragma unroll 1
+      for (int h = 0; h < nsteps; h += 2) {
+        tmem_ld_wait();
+        if (h + 1 < nsteps) tmem_ld_32x32b_x32(treg + 32 * (h + 1), rb);
+        exp32(ra, h);
+        if (h + 1 < nsteps) {
+          tmem_ld_wait();
+          if (h + 2 < nsteps) tmem_ld_32x32b_x32(treg + 32 * (h + 2), ra);
+          exp32(rb, h + 1);
+        }
       }
       float l = (ps0 + ps1) + (ps2 + ps3);
       if (leftover) {
