@@ -7,18 +7,23 @@
 // ~2800 cycles per chunk, of which ~1300 are barrier hops and MMA issue).  Here:
 //   * one persistent CTA per SM walks (image, head) pairs; K, V and Q of a pair are loaded ONCE (TMA, 2-stage ring, the
 //     next pair's loads fly during the current pair's math);
-//   * two 128-row query tiles (A, B) per pair, one softmax thread per row (warps 0-3: tile A, 4-7: tile B);
+//   * two 128-row query tiles (A, B) per pair, TWO softmax threads per row: warp (t, q, kh) owns rows q*32..q*32+31 of tile t and
+//     the keys [128 kh, 128 kh + 128); the two halves of a row sit on the same SM sub-partition, so one warp's exponentials
+//     (MUFU: 16 results/clk/SM, measured: tools/micro/mufu_rate.cu) run under the other's tensor-memory loads / stores -- a lone
+//     warp per sub-partition serialises on every tcgen05.ld / wait / st (155 -> 135 us per layer at B = 256);
 //   * S = Q K^T for 256 keys is ONE accumulator of 128 x 256 fp32 = 256 tensor-memory columns per tile (4 MMAs of N = 256):
-//     exact two-pass softmax (row maximum, then exp2 / sum) straight from tensor memory -- no online rescaling, no O
-//     correction pass, three hand-shakes per tile instead of ten;
-//   * P (bf16 pairs) is written back over the consumed S columns [0, 128) and feeds the P.V MMA as its tensor-memory
-//     A operand; O lands in columns [128, 192) of the same region (S is dead by then): 2 tiles x 256 columns = all of TMEM;
-//   * T = 257 = 256 + 1: the 257th KEY is a 16-column MMA (N = 16: Q . [k_256; 0]^T) read before the region is reused
-//     plus one extra k-step of the P.V product; the 257th QUERY ROW is scored as S^T = K . [q_256; 0]^T (keys along the
-//     TMEM lanes, so 256 threads read one score each), soft-maxed by one auxiliary warp, and its P.V (257 x 64 FMAs) is
-//     split over the eight softmax warps on the CUDA cores.  No third query tile, no fifth key chunk.
-// Warp roles (352 threads): 0-3 softmax tile A, 4-7 softmax tile B, 8 auxiliary (257th row), 9 TMA producer, 10 MMA issuer
-// (highest warp id: the issue arbiter favours it).
+//     exact two-pass softmax (row maximum, then exp2 / sum) straight from tensor memory in 32-key steps -- no online rescaling,
+//     no O correction pass; the halves of a row exchange their maximum and their sum through shared memory + a 64-thread named
+//     barrier (both add (half 0) + (half 1): identical bits);
+//   * P (bf16 pairs) is written back over score columns the SAME warp has already consumed -- keys [0, 128) -> columns [0, 64),
+//     keys [128, 256) -> columns [128, 192) -- and feeds the P.V MMA as its tensor-memory A operand; O lands in columns [192, 256)
+//     of the same region (S is dead by then): 2 tiles x 256 columns = all of TMEM;
+//   * T = 257 = 256 + 1: the 257th KEY is a 16-column MMA (N = 16: Q . [k_256; 0]^T) into spare columns [80, 96) (scores of keys
+//     64..127 of the previous pair, consumed) plus one extra k-step of the P.V product (its P pair at column 64); the 257th QUERY
+//     ROW is scored as S^T = K . [q_256; 0]^T (keys along the TMEM lanes, columns [96, 128)), soft-maxed by one auxiliary warp,
+//     and its P.V (257 x 64 FMAs) is split over the eight kh = 1 warps on the CUDA cores.  No third query tile, no fifth key chunk.
+// Warp roles (608 threads, 92 registers): 0-3 / 4-7 tile A / B keys [0, 128), 8-11 / 12-15 tile A / B keys [128, 256), 16 auxiliary
+// (257th row), 17 TMA producer, 18 MMA issuer (highest warp id: the issue arbiter favours it).
 #include "common.cuh"
 
 namespace setok {
@@ -28,8 +33,8 @@ int g_attn_fullrow = 1;
 int g_attn_fullrow_dbg = 0;   // timing experiments only (results are wrong): 1 skip pass 1, 2 no exp2, 4 no P store, 8 no O store
 namespace {
 
-constexpr int FR_THREADS = 352;
-constexpr int FR_W_AUX = 8, FR_W_TMA = 9, FR_W_MMA = 10;
+constexpr int FR_THREADS = 608;
+constexpr int FR_W_AUX = 16, FR_W_TMA = 17, FR_W_MMA = 18;
 constexpr int FR_TILE_BYTES = 256 * 128;                 // 256 rows x 64 bf16
 constexpr int FR_X_BYTES = 16 * 128;                     // 16-row boxes holding the 257th q / k / v row (+ zero fill)
 constexpr int FR_OFF_Q = 0, FR_OFF_K = FR_TILE_BYTES, FR_OFF_V = 2 * FR_TILE_BYTES;
@@ -40,12 +45,14 @@ constexpr int FR_OFF_SLEFT = FR_STAGES * FR_STAGE_BYTES;              // float s
 constexpr int FR_PLEFT_STRIDE = 264;                                   // floats per buffer: p[0..256], inv_l at [257]
 constexpr int FR_OFF_PLEFT = FR_OFF_SLEFT + 256 * 4;                  // float p_left[2][264]
 constexpr int FR_OFF_PART = FR_OFF_PLEFT + 2 * FR_PLEFT_STRIDE * 4;   // float part[8][64]
-constexpr int FR_OFF_STG = FR_OFF_PART + 8 * 64 * 4;                  // O staging: 8 warps x 16 rows x 128 B
-constexpr int FR_OFF_BAR = FR_OFF_STG + 8 * 2048;
+constexpr int FR_OFF_STG = FR_OFF_PART + 8 * 64 * 4;                  // O staging: 16 warps x 16 rows x 64 B (also the partner exchange slots)
+constexpr int FR_OFF_BAR = FR_OFF_STG + 16 * 1024;
 constexpr int FR_NUM_BARS = 4 * FR_STAGES + 10 + 3;
 constexpr int FR_SMEM_BYTES = FR_OFF_BAR + FR_NUM_BARS * 8 + 16 + 1024;
 // tensor-memory columns inside a tile's 256-column region
-constexpr uint32_t FR_COL_O = 128, FR_COL_PX = 192, FR_COL_E = 208, FR_COL_L0 = 224, FR_COL_L1 = 240;
+// P of keys [0, 128) over columns [0, 64) and of keys [128, 256) over [128, 192): each half is written by the warp that consumed
+// exactly those score columns; the 257th-key / 257th-row extras sit in [64, 128) (scores of keys 64..127, consumed by then)
+constexpr uint32_t FR_COL_P1 = 128, FR_COL_O = 192, FR_COL_PX = 64, FR_COL_E = 80, FR_COL_L0 = 96, FR_COL_L1 = 112;
 
 __device__ __forceinline__ float fr_exp2(float x) {      // MUFU.EX2; exp2(-inf) = 0
   float y;
@@ -112,7 +119,7 @@ attn_fullrow_hd64_kernel(const __grid_constant__ CUtensorMap tm256, const __grid
       mbar_init(v_full(s), 1); mbar_init(v_empty(s), leftover ? 2 : 1);
     }
     for (int t = 0; t < 2; ++t) mbar_init(e_full(t), 1);
-    for (int t = 0; t < 2; ++t) { mbar_init(s_full(t), 1); mbar_init(p_full(t), 4); mbar_init(o_full(t), 1); mbar_init(o_read(t), 4); }
+    for (int t = 0; t < 2; ++t) { mbar_init(s_full(t), 1); mbar_init(p_full(t), 8); mbar_init(o_full(t), 1); mbar_init(o_read(t), 8); }
     mbar_init(left_s, 4); mbar_init(left_p, 1); mbar_init(left_o, 8);
     fence_mbar_init();
   }
@@ -200,11 +207,12 @@ attn_fullrow_hd64_kernel(const __grid_constant__ CUtensorMap tm256, const __grid
         const uint64_t dv = umma_desc_mn_sw128(sb + FR_OFF_V), dvx = umma_desc_mn_sw128(sb + FR_OFF_VX);
         const uint32_t d = tmem_base + 256u * t;
         if (elect_one_sync()) {
+          // P columns: 8 per k-step, keys [0, 128) from column 0, keys [128, 256) from column FR_COL_P1
           if (ksteps == 16) {
 #pragma unroll
-            for (int k = 0; k < 16; ++k) umma_f16_ts(d + FR_COL_O, d + 8u * k, dv + 128ull * k, idesc_pv, k != 0 ? 1u : 0u);
+            for (int k = 0; k < 16; ++k) umma_f16_ts(d + FR_COL_O, d + 8u * k + (k >= 8 ? FR_COL_P1 - 64u : 0u), dv + 128ull * k, idesc_pv, k != 0 ? 1u : 0u);
           } else {
-            for (int k = 0; k < ksteps; ++k) umma_f16_ts(d + FR_COL_O, d + 8u * k, dv + 128ull * k, idesc_pv, k != 0 ? 1u : 0u);
+            for (int k = 0; k < ksteps; ++k) umma_f16_ts(d + FR_COL_O, d + 8u * k + (k >= 8 ? FR_COL_P1 - 64u : 0u), dv + 128ull * k, idesc_pv, k != 0 ? 1u : 0u);
           }
           if (leftover) umma_f16_ts(d + FR_COL_O, d + FR_COL_PX, dvx, idesc_pv, 1u);
           umma_commit(o_full(t));
@@ -293,14 +301,25 @@ attn_fullrow_hd64_kernel(const __grid_constant__ CUtensorMap tm256, const __grid
         if (lane == 0) mbar_arrive(v_empty(n & 1));          // all CUDA-core readers of this pair's V are done
       }
     }
-  } else if ((warp >> 2) < ntiles) {
+  } else if (warp < 16 && ((warp >> 2) & 1) < ntiles) {
     // ------------------------------------------------ softmax warps ------------------------------------------------
-    const int t = warp >> 2;                                 // query tile
+    // Two threads per query row: warp (t, q, kh) owns rows q*32 .. q*32+31 of tile t and the keys [128 kh, 128 kh + 128).  A lone
+    // warp per SM sub-partition cannot overlap its own MUFU, tensor-memory and ALU work (tcgen05.ld / wait / st serialise it);
+    // with the two halves of a row on the same sub-partition one warp's exponentials run under the other's loads and stores.
+    // The halves meet twice per pair through their staging slots and a 64-thread named barrier: row maximum, row sum.
+    const int t = (warp >> 2) & 1;                           // query tile
+    const int kh = warp >> 3;                                // key half
     const int q = warp & 3;                                  // TMEM lane quarter
     const int row = q * 32 + lane;                           // row within the tile == TMEM lane
     const uint32_t treg = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + 256u * t;
     const float sl2 = p.scale_log2;
     const bool masked = nkeys < 256;
+    const int k_lo = 128 * kh;
+    const int k_hi = Nk < k_lo + 128 ? Nk : k_lo + 128;
+    const int nsteps = k_hi > k_lo ? (k_hi - k_lo + 31) >> 5 : 0;      // 32-key steps of this half
+    float* my_x = reinterpret_cast<float*>(smem + FR_OFF_STG + warp * 1024);          // exchange slots alias the O staging
+    const float* peer_x = reinterpret_cast<const float*>(smem + FR_OFF_STG + (warp ^ 8) * 1024);
+    const int pair_bar = 1 + (warp & 7);                     // named barrier of the two warps that share these rows
     float inv_l = 0.f;
     for (int n = 0; n_local > 0 && n <= n_local; ++n) {
       const int g = static_cast<int>(blockIdx.x) + (n - 1) * static_cast<int>(gridDim.x);     // pair whose O is drained now
@@ -308,8 +327,8 @@ attn_fullrow_hd64_kernel(const __grid_constant__ CUtensorMap tm256, const __grid
       FR_TRACE(t, 0);
       tcgen05_fence_after();
       float s_x = -INFINITY;
-      if (leftover && n < n_local) {
-        // scores against the 257th key (this row) and of the 257th row (this lane's key), parked in the region's tail
+      if (leftover && kh == 0 && n < n_local) {
+        // scores against the 257th key (this row) and of the 257th row (this lane's key), parked in the region's spare columns
         mbar_wait(e_full(t), n & 1);
         tcgen05_fence_after();
         s_x = __uint_as_float(tmem_ld_32x32b_x1(treg + FR_COL_E));
@@ -323,50 +342,47 @@ attn_fullrow_hd64_kernel(const __grid_constant__ CUtensorMap tm256, const __grid
           tmem_ld_wait();
         }
       }
-      uint4 ov[8];
+      uint4 ov[4];
       if (n > 0) {
-        // O(n-1) / l -> bf16, held in registers so that the region can be handed back before anything is stored
+        // this half's 32 dims of O(n-1) / l -> bf16, held in registers so that the region can be handed back before anything is stored
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(treg + FR_COL_O + 32 * kh, o);
+        tmem_ld_wait();
 #pragma unroll
-        for (int c0 = 0; c0 < 64; c0 += 32) {
-          uint32_t o[32];
-          tmem_ld_32x32b_x32(treg + FR_COL_O + c0, o);
-          tmem_ld_wait();
-#pragma unroll
-          for (int v4 = 0; v4 < 4; ++v4) {
-            ov[c0 / 8 + v4].x = pack_bf16x2(__uint_as_float(o[8 * v4 + 0]) * inv_l, __uint_as_float(o[8 * v4 + 1]) * inv_l);
-            ov[c0 / 8 + v4].y = pack_bf16x2(__uint_as_float(o[8 * v4 + 2]) * inv_l, __uint_as_float(o[8 * v4 + 3]) * inv_l);
-            ov[c0 / 8 + v4].z = pack_bf16x2(__uint_as_float(o[8 * v4 + 4]) * inv_l, __uint_as_float(o[8 * v4 + 5]) * inv_l);
-            ov[c0 / 8 + v4].w = pack_bf16x2(__uint_as_float(o[8 * v4 + 6]) * inv_l, __uint_as_float(o[8 * v4 + 7]) * inv_l);
-          }
+        for (int v4 = 0; v4 < 4; ++v4) {
+          ov[v4].x = pack_bf16x2(__uint_as_float(o[8 * v4 + 0]) * inv_l, __uint_as_float(o[8 * v4 + 1]) * inv_l);
+          ov[v4].y = pack_bf16x2(__uint_as_float(o[8 * v4 + 2]) * inv_l, __uint_as_float(o[8 * v4 + 3]) * inv_l);
+          ov[v4].z = pack_bf16x2(__uint_as_float(o[8 * v4 + 4]) * inv_l, __uint_as_float(o[8 * v4 + 5]) * inv_l);
+          ov[v4].w = pack_bf16x2(__uint_as_float(o[8 * v4 + 6]) * inv_l, __uint_as_float(o[8 * v4 + 7]) * inv_l);
         }
       }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(o_read(t));                              // the region may take the next S
-        if (leftover && t == 0 && n < n_local) mbar_arrive(left_s);
+        mbar_arrive(o_read(t));                              // the region may take the next S (once all eight warps of the tile are here)
+        if (leftover && t == 0 && kh == 0 && n < n_local) mbar_arrive(left_s);
       }
       FR_TRACE(t, 1);
       if (n > 0) {
-        // rows -> global through this warp's 2 KiB of staging, 16 rows per round: a thread owns a row in tensor memory, but a
-        // coalesced store wants 8 lanes on one 128-byte row; both shared-memory sides are conflict-free (XOR swizzle)
+        // rows -> global through this warp's 1 KiB of staging, 16 rows x 64 B per round: a thread owns a row in tensor memory, but
+        // a coalesced store wants 4 lanes on one 64-byte half row; both shared-memory sides are conflict-free (XOR swizzle)
         const int b = g / p.heads, h = g % p.heads;
-        uint8_t* stg = smem + FR_OFF_STG + warp * 2048;
+        uint8_t* stg = smem + FR_OFF_STG + warp * 1024;
 #pragma unroll
         for (int rnd = 0; rnd < 2; ++rnd) {
           if ((lane >> 4) == rnd) {
             const int lr = lane & 15;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(stg + lr * 128 + ((c ^ (lr & 7)) << 4)) = ov[c];
+            for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(stg + lr * 64 + ((c ^ ((lr >> 1) & 3)) << 4)) = ov[c];
           }
           __syncwarp();
           if (!(p.dbg & 8)) {
 #pragma unroll
-            for (int it = 0; it < 4; ++it) {
-              const int lr = it * 4 + (lane >> 3), c = lane & 7;
-              const uint4 v = *reinterpret_cast<const uint4*>(stg + lr * 128 + ((c ^ (lr & 7)) << 4));
+            for (int it = 0; it < 2; ++it) {
+              const int lr = it * 8 + (lane >> 2), c = lane & 3;
+              const uint4 v = *reinterpret_cast<const uint4*>(stg + lr * 64 + ((c ^ ((lr >> 1) & 3)) << 4));
               const int grow = t * 128 + q * 32 + rnd * 16 + lr;
-              if (grow < T) *reinterpret_cast<uint4*>(p.out + (static_cast<long long>(b) * T + grow) * C + h * 64 + c * 8) = v;
+              if (grow < T) *reinterpret_cast<uint4*>(p.out + (static_cast<long long>(b) * T + grow) * C + h * 64 + kh * 32 + c * 8) = v;
             }
           }
           __syncwarp();
@@ -378,48 +394,42 @@ attn_fullrow_hd64_kernel(const __grid_constant__ CUtensorMap tm256, const __grid
       mbar_wait(s_full(t), n & 1);
       FR_TRACE(t, 3);
       tcgen05_fence_after();
-      // Both passes walk the row in 32-key steps with two register buffers: the tcgen05.ld of step h + 1 is issued right after
-      // the wait for step h and flies under step h's arithmetic (tcgen05.wait::ld covers every outstanding load, so the order
-      // is wait -> issue next -> compute), instead of one exposed tensor-memory round trip per 64-key chunk.
-      const int nsteps = (Nk + 31) >> 5;
-      uint32_t ra[32], rb[32];
-      // pass 1: row maximum over the keys
+      uint32_t r[32];
+      // pass 1: maximum over this half's keys, then over the row through the partner's slot
       float mx0 = s_x, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-      auto max32 = [&](uint32_t (&r)[32], int h) {
-        if (masked) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) if (32 * h + i >= nkeys) r[i] = 0xff800000u;
-        }
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          mx0 = fmaxf(mx0, __uint_as_float(r[i])); mx1 = fmaxf(mx1, __uint_as_float(r[i + 1]));
-          mx2 = fmaxf(mx2, __uint_as_float(r[i + 2])); mx3 = fmaxf(mx3, __uint_as_float(r[i + 3]));
-        }
-      };
       if (!(p.dbg & 1)) {
-        tmem_ld_32x32b_x32(treg, ra);
 #pragma unroll 1
-        for (int h = 0; h < nsteps; h += 2) {
+        for (int hs = 0; hs < nsteps; ++hs) {
+          const int k0 = k_lo + 32 * hs;
+          tmem_ld_32x32b_x32(treg + k0, r);
           tmem_ld_wait();
-          if (h + 1 < nsteps) tmem_ld_32x32b_x32(treg + 32 * (h + 1), rb);
-          max32(ra, h);
-          if (h + 1 < nsteps) {
-            tmem_ld_wait();
-            if (h + 2 < nsteps) tmem_ld_32x32b_x32(treg + 32 * (h + 2), ra);
-            max32(rb, h + 1);
+          if (masked) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (k0 + i >= nkeys) r[i] = 0xff800000u;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            mx0 = fmaxf(mx0, __uint_as_float(r[i])); mx1 = fmaxf(mx1, __uint_as_float(r[i + 1]));
+            mx2 = fmaxf(mx2, __uint_as_float(r[i + 2])); mx3 = fmaxf(mx3, __uint_as_float(r[i + 3]));
           }
         }
       }
+      my_x[lane] = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      named_bar_sync(pair_bar, 64);
+      const float m = (p.dbg & 1) ? 8.0f : fmaxf(my_x[lane], peer_x[lane]) * sl2;
       FR_TRACE(t, 4);
-      const float m = (p.dbg & 1) ? 8.0f : fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sl2;
       const bool no_exp = (p.dbg & 2) != 0;
-      // pass 2: p = exp2(s * scale - m); P (bf16 pairs) goes back over the S columns already consumed: the 16 columns of step h
-      // lie inside step floor(h / 2)'s score columns, which are in registers or done with by then
+      // pass 2: p = exp2(s * scale - m); P (bf16 pairs) goes back over score columns this warp has already consumed (the 16
+      // columns of step hs lie inside the columns of step hs / 2 of the same half)
       float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
-      auto exp32 = [&](uint32_t (&r)[32], int h) {
+#pragma unroll 1
+      for (int hs = 0; hs < nsteps; ++hs) {
+        const int k0 = k_lo + 32 * hs;
+        tmem_ld_32x32b_x32(treg + k0, r);
+        tmem_ld_wait();
         if (masked) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) if (32 * h + i >= nkeys) r[i] = 0xff800000u;
+          for (int i = 0; i < 32; ++i) if (k0 + i >= nkeys) r[i] = 0xff800000u;
         }
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
@@ -430,50 +440,44 @@ attn_fullrow_hd64_kernel(const __grid_constant__ CUtensorMap tm256, const __grid
           r[i / 2] = pack_bf16x2(p0, p1);               // in place: slots <= i/2+1 were consumed already
           r[i / 2 + 1] = pack_bf16x2(p2, p3);
         }
-        if (!(p.dbg & 4)) tmem_st_32x32b_x16(treg + 16 * h, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
-      };
-      tmem_ld_32x32b_x32(treg, ra);
-#pragma unroll 1
-      for (int h = 0; h < nsteps; h += 2) {
-        tmem_ld_wait();
-        if (h + 1 < nsteps) tmem_ld_32x32b_x32(treg + 32 * (h + 1), rb);
-        exp32(ra, h);
-        if (h + 1 < nsteps) {
-          tmem_ld_wait();
-          if (h + 2 < nsteps) tmem_ld_32x32b_x32(treg + 32 * (h + 2), ra);
-          exp32(rb, h + 1);
-        }
+        if (!(p.dbg & 4)) tmem_st_32x32b_x16(treg + (kh ? FR_COL_P1 : 0u) + 16 * hs, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
       }
       float l = (ps0 + ps1) + (ps2 + ps3);
-      if (leftover) {
+      if (leftover && kh == 0) {
         const float p_x = fr_exp2(fmaf(s_x, sl2, -m));
         l += p_x;
         uint32_t px[8] = {pack_bf16x2(p_x, 0.f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
         tmem_st_32x32b_x8(treg + FR_COL_PX, px);
       }
-      inv_l = 1.0f / l;
+      my_x[32 + lane] = l;
+      named_bar_sync(pair_bar, 64);
+      {
+        const float lp = peer_x[32 + lane];
+        inv_l = 1.0f / (kh == 0 ? l + lp : lp + l);       // both halves add (half 0) + (half 1) in that order: identical bits
+      }
       tmem_st_wait();
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full(t));
       FR_TRACE(t, 5);
 
-      if (leftover) {
+      if (leftover && kh == 1) {
         // this warp's 32-key slice of the 257th row's P.V on the CUDA cores: lane <-> dims (2 lane, 2 lane + 1)
+        const int sl = warp & 7;
         mbar_wait(v_full(n & 1), (n >> 1) & 1);
         mbar_wait(left_p, n & 1);
-        const float* pl = p_left + (n & 1) * FR_PLEFT_STRIDE + 32 * warp;
+        const float* pl = p_left + (n & 1) * FR_PLEFT_STRIDE + 32 * sl;
         const uint8_t* vt = smem + (n & 1) * FR_STAGE_BYTES + FR_OFF_V;
         float a0 = 0.f, a1 = 0.f;
 #pragma unroll 8
         for (int jj = 0; jj < 32; ++jj) {
-          const int r = 32 * warp + jj;
-          const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(vt + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4));
+          const int rr = 32 * sl + jj;
+          const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(vt + rr * 128 + (((lane >> 2) ^ (rr & 7)) << 4) + (lane & 3) * 4));
           const float pj = pl[jj];
           a0 = fmaf(pj, v.x, a0);
           a1 = fmaf(pj, v.y, a1);
         }
-        *reinterpret_cast<float2*>(part + warp * 64 + 2 * lane) = make_float2(a0, a1);
+        *reinterpret_cast<float2*>(part + sl * 64 + 2 * lane) = make_float2(a0, a1);
         __syncwarp();
         if (lane == 0) mbar_arrive(left_o);
         FR_TRACE(t, 6);
