@@ -326,22 +326,6 @@ attn_fullrow_hd64_kernel(const __grid_constant__ CUtensorMap tm256, const __grid
       mbar_wait(o_full(t), n & 1);
       FR_TRACE(t, 0);
       tcgen05_fence_after();
-      float s_x = -INFINITY;
-      if (leftover && kh == 0 && n < n_local) {
-        // scores against the 257th key (this row) and of the 257th row (this lane's key), parked in the region's spare columns
-        mbar_wait(e_full(t), n & 1);
-        tcgen05_fence_after();
-        s_x = __uint_as_float(tmem_ld_32x32b_x1(treg + FR_COL_E));
-        if (t == 0) {
-          const float l0 = __uint_as_float(tmem_ld_32x32b_x1(treg + FR_COL_L0));
-          const float l1 = __uint_as_float(tmem_ld_32x32b_x1(treg + FR_COL_L1));
-          tmem_ld_wait();
-          s_left[row] = l0;
-          s_left[128 + row] = l1;
-        } else {
-          tmem_ld_wait();
-        }
-      }
       uint4 ov[4];
       if (n > 0) {
         // this half's 32 dims of O(n-1) / l -> bf16, held in registers so that the region can be handed back before anything is stored
@@ -354,6 +338,23 @@ attn_fullrow_hd64_kernel(const __grid_constant__ CUtensorMap tm256, const __grid
           ov[v4].y = pack_bf16x2(__uint_as_float(o[8 * v4 + 2]) * inv_l, __uint_as_float(o[8 * v4 + 3]) * inv_l);
           ov[v4].z = pack_bf16x2(__uint_as_float(o[8 * v4 + 4]) * inv_l, __uint_as_float(o[8 * v4 + 5]) * inv_l);
           ov[v4].w = pack_bf16x2(__uint_as_float(o[8 * v4 + 6]) * inv_l, __uint_as_float(o[8 * v4 + 7]) * inv_l);
+        }
+      }
+      float s_x = -INFINITY;
+      if (leftover && kh == 0 && n < n_local) {
+        // scores against the 257th key (this row) and of the 257th row (this lane's key), parked in the region's spare columns by
+        // MMAs that run behind the P.V in the tensor pipe (hence after the O drain: their barrier fires later than o_full)
+        mbar_wait(e_full(t), n & 1);
+        tcgen05_fence_after();
+        s_x = __uint_as_float(tmem_ld_32x32b_x1(treg + FR_COL_E));
+        if (t == 0) {
+          const float l0 = __uint_as_float(tmem_ld_32x32b_x1(treg + FR_COL_L0));
+          const float l1 = __uint_as_float(tmem_ld_32x32b_x1(treg + FR_COL_L1));
+          tmem_ld_wait();
+          s_left[row] = l0;
+          s_left[128 + row] = l1;
+        } else {
+          tmem_ld_wait();
         }
       }
       tcgen05_fence_before();
