@@ -20,7 +20,8 @@ def main():
         tok = setok_b200.SetokTokenizer("siglip-synthetic-vit-l-14", vision_config=dict(bench.VIT, image_size=224), tower_ln_fold=fold, **bench.HEAD)
         towers[name] = tok.to(dev).image_feature_encoder
     from setok_b200.synth import mondrian_images
-    images = mondrian_images(256, 224, 1234, "cpu").to(dev)
+    nimg = int(os.environ.get("IMAGES", "256"))
+    images = mondrian_images(nimg, 224, 1234, "cpu").to(dev)
     out = {k: t(images) for k, t in towers.items()}
     d = (out["folded"] - out["separate"]).float()
     print(f"folded vs separate: rel-Frobenius {float(d.norm() / out['separate'].float().norm()):.3e}, "
@@ -45,7 +46,7 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / reps
-            print(f"round {rnd} {name:9s}: tower {ms:7.2f} ms per 256 images = {256 / ms * 1e3:7.1f} images/s", flush=True)
+            print(f"round {rnd} {name:9s}: tower {ms:7.2f} ms per {nimg} images = {nimg / ms * 1e3:7.1f} images/s", flush=True)
 
 
 if __name__ == "__main__":
