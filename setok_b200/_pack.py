@@ -45,3 +45,15 @@ class PackedParams:
 
     def invalidate(self):
         self._packed = None
+
+
+def fold_layernorm_into_linear(w: torch.Tensor, b: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor):
+    """What SETOK_VIT_LN_FOLD packs for a Linear that follows a LayerNorm (include/setok_b200.h): ``LN(x) W^T + b`` is evaluated by the
+    GEMM as ``(rho / r) * (xhat W'^T)_n - rho * m * s_n + t_n`` with xhat = (x - c) r the stream normalised by lagged statistics
+    (c, r), m = mean(x - c), rho = rsqrt(var + eps).  Returns (W' = bf16(W diag(gamma)), s = row sums of the ROUNDED W' -- the mean
+    correction must cancel exactly against what the tensor cores multiply --, t = W beta + b), all computed in float32."""
+    w = w.float()
+    wg = (w * gamma.float()[None, :]).to(torch.bfloat16).contiguous()
+    s = wg.float().sum(1).contiguous()
+    t = ((w * beta.float()[None, :]).sum(1) + b.float()).contiguous()
+    return wg, s, t

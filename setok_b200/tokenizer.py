@@ -32,7 +32,7 @@ import torch.nn as nn
 
 from . import _lib, ops
 from ._lib import SetokError
-from ._pack import PackedParams, stamp
+from ._pack import PackedParams, fold_layernorm_into_linear, stamp
 from .ragged import RaggedTokens
 
 
@@ -230,10 +230,7 @@ class CLIPVisionTower(PackedParams, nn.Module):
                 if fold:
                     # LN(x) W^T + b = rho (x - mu) (gamma (.) W)^T + (W beta + b): the GEMM runs on W' = bf16(gamma (.) W), its
                     # epilogue needs s_n = sum_k W'_nk (of the ROUNDED matrix: the mean correction cancels exactly) and t = W beta + b
-                    wg = (w32_ * t[g_][None, :]).to(torch.bfloat16).contiguous()
-                    t[s_] = wg.float().sum(1).contiguous()
-                    t[b_] = ((w32_ * t[be_][None, :]).sum(1) + t[b_]).contiguous()
-                    t[w_] = wg
+                    t[w_], t[s_], t[b_] = fold_layernorm_into_linear(w32_, t[b_], t[g_], t[be_])
                 else:
                     t[w_] = w32_.to(torch.bfloat16).contiguous()
             for k_, v in t.items():

@@ -122,3 +122,34 @@ def test_u8_normalisation_constants_reproduce_the_hf_processor():
         assert y.dtype == np.float32 and np.array_equal(ours[i], np.transpose(y, (2, 0, 1)))
     fast = ip.preprocess(list(img), return_tensors="np", input_data_format="channels_last")["pixel_values"]
     assert np.abs(ours - fast).max() <= 2.4e-7 * np.abs(fast).max()
+
+
+def test_layernorm_fold_algebra_on_cpu():
+    """The host half of SETOK_VIT_LN_FOLD (setok_b200/_pack.py:fold_layernorm_into_linear) and the epilogue formulas of
+    include/setok_b200.h, evaluated in torch on the CPU: with ANY lagged statistics (c, r) the consuming-side formula reproduces
+    LayerNorm(x) W^T + b up to the bf16 rounding of xhat and W' (no GPU involved: this pins the algebra, the GPU tests pin the kernels)."""
+    import torch
+    from setok_b200._pack import fold_layernorm_into_linear
+    g = torch.Generator().manual_seed(5)
+    M, C, N, eps = 64, 256, 96, 1e-5
+    x = torch.randn(M, C, generator=g) * (0.5 + 3 * torch.rand(M, 1, generator=g)) + 2 * torch.randn(M, 1, generator=g)
+    gamma, beta = 1 + 0.3 * torch.randn(C, generator=g), 0.3 * torch.randn(C, generator=g)
+    w, b = torch.randn(N, C, generator=g) * C ** -0.5, 0.1 * torch.randn(N, generator=g)
+    ref = torch.nn.functional.layer_norm(x.double(), (C,), gamma.double(), beta.double(), eps) @ w.double().t() + b.double()
+    wg, s, t = fold_layernorm_into_linear(w, b, gamma, beta)
+    assert wg.dtype == torch.bfloat16 and torch.equal(s, wg.float().sum(1))
+    for lag in (0.0, 0.3, -1.0):                    # how far the lagged mean / scale are from the row's true ones
+        c = x.mean(1) + lag * x.std(1)
+        r = (x.var(1, unbiased=False) * (1 + lag) ** 2 + eps).rsqrt()
+        d = x - c[:, None]
+        xhat = (d * r[:, None]).to(torch.bfloat16)                       # producing side
+        parts = torch.stack([d[:, i:i + 128].sum(1) for i in range(0, C, 128)], 1), torch.stack([(d[:, i:i + 128] ** 2).sum(1) for i in range(0, C, 128)], 1)
+        m = parts[0].sum(1) / C                                          # consuming side
+        var = parts[1].sum(1) / C - m * m
+        rho = (var + eps).rsqrt()
+        acc = xhat.float() @ wg.float().t()
+        y = (rho / r)[:, None] * acc + (-rho * m)[:, None] * s[None, :] + t[None, :]
+        err = float((y.double() - ref).abs().max() / ref.abs().max())
+        assert err < 8e-3, (lag, err)                                    # bf16 operands: 2^-9 relative per element
+        exact = (rho[:, None] * (d - m[:, None])) * gamma + beta        # the same identity without any rounding
+        assert torch.allclose(exact.double() @ w.double().t() + b.double(), ref, rtol=1e-4, atol=1e-4)

@@ -12,7 +12,9 @@ tests/test_gpu_dpc.py::test_dpc_golden_bit_exact tests/test_gpu_model.py::test_h
 tests/test_gpu_preprocess.py::test_golden_cases_bit_exact tests/test_gpu_splice.py tests/test_gpu_detok.py::test_detok_golden \
 tests/test_gpu_kernels.py::test_gemm_epilogues"
 # both GEMM epilogues (row-owner / transposing) on the small shapes
-KEXPR="row_owner and (391 or 77-96 or 1-32)"
+KEXPR="(row_owner and (391 or 77-96 or 1-32)) or (fold_chain and (65-128 or 160-96 or 300-1024))"
+# the LayerNorm-fold tower (both producing epilogues, the fused pre-LN record) and the vector im2col
+MEXPR="fold_matches or im2col_vector"
 rc=0
 for tool in memcheck racecheck synccheck; do
   echo "== compute-sanitizer --tool $tool"
@@ -24,6 +26,10 @@ for tool in memcheck racecheck synccheck; do
       python -m pytest tests/test_gpu_kernels.py -k "$KEXPR" -m gpu -q -x -p no:cacheprovider >> "$OUT/$tool.log" 2>&1
   r2=$?
   [ $r2 -ne 0 ] && r=$r2
+  timeout 900 "$CS" --tool "$tool" --error-exitcode 9 --launch-timeout 120 \
+      python -m pytest tests/test_gpu_model.py -k "$MEXPR" -m gpu -q -x -p no:cacheprovider >> "$OUT/$tool.log" 2>&1
+  r3=$?
+  [ $r3 -ne 0 ] && r=$r3
   tail -4 "$OUT/$tool.log"
   grep -E "ERROR SUMMARY|RACECHECK SUMMARY" "$OUT/$tool.log" | tail -2
   [ $r -ne 0 ] && rc=$r
