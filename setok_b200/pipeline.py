@@ -128,7 +128,8 @@ def stream_tokenize(tokenizer, host_batches: Iterable[Tuple[torch.Tensor, Option
     reads = deque()                      # read-backs in flight, oldest first
     while nxt is not None:
         d_img, d_noise, ev = nxt
-        main.wait_event(ev)
+        if not ev.query():                  # the upload was issued a whole batch ago: normally complete, and then the compute
+            main.wait_event(ev)             # stream needs no cross-stream wait in front of the batch's first kernel
         d_img.record_stream(main)
         if d_noise is not None:
             d_noise.record_stream(main)
