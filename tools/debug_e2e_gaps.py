@@ -57,5 +57,75 @@ def main():
         T.report("streamed, uint8 images")
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) == 1:
     main()
+
+
+def variants():
+    """Which ingredient of the streamed loop opens the ~0.3 ms gap at a batch boundary?  The resident loop plus one ingredient at a time."""
+    dev = torch.device("cuda:0")
+    tok = bench.build_model(dev)
+    u8, imgs_h, noise_h = bench.host_batch(2, 0)
+    noise = noise_h.to(dev)
+    d_u8 = u8.to(dev)
+    h_u8 = u8.pin_memory()
+    side, copy = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    main = torch.cuda.current_stream(dev)
+    T = Timed(tok)
+    n = 14
+    pinned = [torch.empty(256, 256, dtype=torch.int64).pin_memory() for _ in range(3)]
+
+    def run(name, after=None, before=None):
+        prev = None
+        for i in range(n):
+            img = before(i) if before else d_u8
+            out = T(img, k=bench.KNN_K, noise=noise)
+            if after:
+                prev = after(i, out, prev)
+        T.report(name)
+
+    run("resident")
+
+    def a1(i, out, prev):
+        e = torch.cuda.Event(); e.record(main); return e
+    run("+ event record", a1)
+
+    def a2(i, out, prev):
+        e = torch.cuda.Event(); e.record(main)
+        side.wait_event(e)
+        with torch.cuda.stream(side):
+            pinned[i % 3].copy_(out[1], non_blocking=True)
+        return e
+    run("+ side-stream D2H after it", a2)
+
+    def a3(i, out, prev):
+        e = torch.cuda.Event(); e.record(main)
+        side.wait_event(e)
+        with torch.cuda.stream(side):
+            pinned[i % 3].copy_(out[1], non_blocking=True)
+            e2 = torch.cuda.Event(); e2.record(side)
+        if prev is not None:
+            prev.synchronize()
+        return e2
+    run("+ host sync one batch behind", a3)
+
+    ups = {}
+
+    def b4(i):
+        with torch.cuda.stream(copy):
+            d = h_u8.to(dev, non_blocking=True)
+            e = torch.cuda.Event(); e.record(copy)
+        ups[i] = (d, e)
+        if i == 0:
+            main.wait_event(e)
+            return d
+        d0, e0 = ups.pop(i - 1)
+        if not e0.query():
+            main.wait_event(e0)
+        d0.record_stream(main)
+        return d0
+    run("+ H2D upload one batch ahead", None, b4)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "variants":
+    variants()
