@@ -325,12 +325,20 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // generic-proxy smem writes -> visible to the async proxy (UMMA / TMA reads)
 // 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one full 32-byte sector per thread per instruction.  The pointer
 // must be 32-byte aligned.
+#ifndef SETOK_EPI_STREAMING
+#define SETOK_EPI_STREAMING 0   // 1: the GEMM epilogues' activation loads / stores carry the evict-first hint (ld/st.global.cs): every activation
+#endif                          // is read once by the next kernel, only the operands the concurrent tiles share are worth keeping in L2
+#if SETOK_EPI_STREAMING
+#define SETOK_CS ".cs"
+#else
+#define SETOK_CS ""
+#endif
 __device__ __forceinline__ void ld_global_v8(const void* p, uint32_t* r) {
-  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+  asm volatile("ld.global" SETOK_CS ".v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
 }
 __device__ __forceinline__ void st_global_v8(void* p, const uint32_t* r) {
-  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+  asm volatile("st.global" SETOK_CS ".v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                :: "l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
 

@@ -45,6 +45,22 @@ template <int CG> struct Cfg {
   static constexpr int SMEM_BYTES = OFF_BAR + NUM_BARS * 8 + 16 + 1024;   // + tmem ptr + alignment slack
 };
 
+// float4 activation accesses of the transposing epilogue, with the evict-first hint under SETOK_EPI_STREAMING
+__device__ __forceinline__ float4 epi_ld4(const float* p) {
+#if SETOK_EPI_STREAMING
+  return __ldcs(reinterpret_cast<const float4*>(p));
+#else
+  return *reinterpret_cast<const float4*>(p);
+#endif
+}
+__device__ __forceinline__ void epi_st4(float* p, float4 v) {
+#if SETOK_EPI_STREAMING
+  __stcs(reinterpret_cast<float4*>(p), v);
+#else
+  *reinterpret_cast<float4*>(p) = v;
+#endif
+}
+
 struct GemmDev {
   void* D; long long ldd;
   const float* bias;
@@ -381,7 +397,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             if (ok) rt[slot][it] = *reinterpret_cast<const uint2*>(static_cast<const bf16*>(p.res) + static_cast<long long>(bt) * p.r_batch_stride + static_cast<long long>(grow) * p.ldr + col);
           } else {
             rtf[slot][it] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok) rtf[slot][it] = *reinterpret_cast<const float4*>(static_cast<const float*>(p.res) + static_cast<long long>(bt) * p.r_batch_stride + static_cast<long long>(grow) * p.ldr + col);
+            if (ok) rtf[slot][it] = epi_ld4(static_cast<const float*>(p.res) + static_cast<long long>(bt) * p.r_batch_stride + static_cast<long long>(grow) * p.ldr + col);
           }
         }
       };
@@ -482,7 +498,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           if (grow < M_eff && col_ok) {
             const long long orow = remap_P > 0 ? (grow + grow / remap_P + 1) : grow;
             if (out_f32) {
-              *reinterpret_cast<float4*>(static_cast<float*>(p.D) + dbase + orow * p.ldd + col) = v;
+              epi_st4(static_cast<float*>(p.D) + dbase + orow * p.ldd + col, v);
             } else {
               *reinterpret_cast<uint2*>(static_cast<bf16*>(p.D) + dbase + orow * p.ldd + col) =
                   make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
