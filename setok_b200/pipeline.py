@@ -26,12 +26,16 @@ from .ragged import RaggedTokens
 class HostResult:
     """Host copy of one batch's output: packed tokens (sum K, C), offsets (B+1,), idx_cluster (B, N), score (B, 1, N)."""
 
-    def __init__(self, tokens, offsets, idx_cluster, score):
+    def __init__(self, tokens, offsets, idx_cluster, score, copied_rows: Optional[int] = None):
         self.tokens, self.offsets, self.idx_cluster, self.score = tokens, offsets, idx_cluster, score
+        # rows that actually crossed the bus (>= len(tokens) when the read-back was sized speculatively)
+        self.copied_rows = int(tokens.shape[0]) if copied_rows is None else int(copied_rows)
 
     @property
     def nbytes(self) -> int:
-        return sum(t.numel() * t.element_size() for t in (self.tokens, self.offsets, self.idx_cluster, self.score))
+        """Bytes copied device -> host for this batch (speculative surplus rows included)."""
+        row = self.tokens.shape[1] * self.tokens.element_size() if self.tokens.dim() == 2 else 0
+        return self.copied_rows * row + sum(t.numel() * t.element_size() for t in (self.offsets, self.idx_cluster, self.score))
 
 
 class _Readback:
@@ -43,11 +47,13 @@ class _Readback:
     `Tensor.record_stream`: a recorded block is not reusable until the allocator has polled the side stream's event, which
     made every step cudaMalloc a fresh capacity-sized buffer -- 134 MB for config 4's projected rows -- inside the step)."""
 
-    def __init__(self, out, d2h: torch.cuda.Stream, after: torch.cuda.Event):
+    def __init__(self, out, d2h: torch.cuda.Stream, after: torch.cuda.Event, guess_rows: int = 0):
         self.rt, self.idx, self.score = out
         self.d2h = d2h
         d2h.wait_event(after)
         known = self.rt._host is not None            # offsets already on the host (RaggedAllGather.finish)
+        self.h_guess = None
+        self.copied = 0
         with torch.cuda.stream(d2h):
             self.h_off = torch.empty(self.rt.offsets.shape, dtype=self.rt.offsets.dtype, pin_memory=True)
             self.h_off.copy_(self.rt.offsets, non_blocking=True)
@@ -58,12 +64,21 @@ class _Readback:
             self.h_tok = None
             if known:
                 self.h_tok = self._rows(self.rt.total)
+            elif guess_rows > 0:
+                # Speculative single hop: a copy the host issues only once it knows the row count is submitted AFTER the next
+                # batch's kernels and, on this platform, is served after them too (measured: the result of batch j came back
+                # when batch j + 1 had finished, and the compute stream idled ~0.3 ms per batch waiting for the host).  So the rows
+                # are copied now, sized by the previous batch's count plus a margin; result() falls back to the second hop only
+                # when this batch turned out larger.
+                n = min(int(guess_rows), int(self.rt.data.shape[0]))
+                self.h_guess = self._rows(n)
             self.ev = torch.cuda.Event()
             self.ev.record(d2h)
 
     def _rows(self, total: int):
         h_tok = torch.empty((total, self.rt.data.shape[1]), dtype=self.rt.data.dtype, pin_memory=True)
         h_tok.copy_(self.rt.data[:total], non_blocking=True)
+        self.copied += total
         return h_tok
 
     def _release(self):
@@ -72,11 +87,15 @@ class _Readback:
     def result(self) -> HostResult:
         self.ev.synchronize()
         if self.h_tok is None:
-            with torch.cuda.stream(self.d2h):
-                self.h_tok = self._rows(int(self.h_off[-1]))
-            self.d2h.synchronize()
+            total = int(self.h_off[-1])
+            if self.h_guess is not None and total <= self.h_guess.shape[0]:
+                self.h_tok = self.h_guess[:total]            # the speculative copy covered the batch: no second hop
+            else:
+                with torch.cuda.stream(self.d2h):
+                    self.h_tok = self._rows(total)
+                self.d2h.synchronize()
         self._release()
-        return HostResult(self.h_tok, self.h_off, self.h_idx, self.h_score)
+        return HostResult(self.h_tok, self.h_off, self.h_idx, self.h_score, copied_rows=self.copied)
 
     def __del__(self):                                # abandoned before result(): the copies may still be reading the tensors
         try:
@@ -116,8 +135,15 @@ def stream_tokenize(tokenizer, host_batches: Iterable[Tuple[torch.Tensor, Option
             ev.record(copy_stream)
         return d_img, d_noise, ev
 
+    state = {"guess": 0}
+
     def read(out, after):
-        return _Readback(out, d2h_stream, after)
+        return _Readback(out, d2h_stream, after, guess_rows=state["guess"])
+
+    def took(res: HostResult) -> HostResult:
+        # next batches' speculative read-back: this batch's row count + 25 %, in whole blocks of 64 rows
+        state["guess"] = max(64, (int(res.tokens.shape[0]) * 5 // 4 + 63) // 64 * 64)
+        return res
 
     it = iter(host_batches)
     try:
@@ -150,11 +176,11 @@ def stream_tokenize(tokenizer, host_batches: Iterable[Tuple[torch.Tensor, Option
             done.record(main)
             reads.append(read(out, done))
         while len(reads) > 1:
-            yield reads.popleft().result()   # an older batch's D2H (and its host sync) overlaps the newer batches' kernels
+            yield took(reads.popleft().result())   # an older batch's D2H (and its host sync) overlaps the newer batches' kernels
     if pending_gather is not None:
         reads.append(_finish_gather(gather, pending_gather, read))
     while reads:
-        yield reads.popleft().result()
+        yield took(reads.popleft().result())
 
 
 def _finish_gather(gather, pending, read):

@@ -129,3 +129,125 @@ def variants():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "variants":
     variants()
+
+
+def variants2():
+    """The real stream_tokenize with pieces of its read-back switched off (monkey-patched), to see which piece opens the gap."""
+    from setok_b200 import pipeline
+    dev = torch.device("cuda:0")
+    tok = bench.build_model(dev)
+    u8, imgs_h, noise_h = bench.host_batch(2, 0)
+    h_u8, h_noise = u8.pin_memory(), noise_h.pin_memory()
+    T = Timed(tok)
+    n = 14
+
+    def run(name):
+        for _ in stream_tokenize(T, ((h_u8, h_noise) for _ in range(n)), k=bench.KNN_K):
+            pass
+        T.report(name)
+
+    run("stream_tokenize as shipped")
+    orig_init, orig_result, orig_rows = pipeline._Readback.__init__, pipeline._Readback.result, pipeline._Readback._rows
+
+    # (a) no second hop: the rows are not copied at all
+    def result_no_rows(self):
+        self.ev.synchronize()
+        self._release()
+        return pipeline.HostResult(self.h_off, self.h_off, self.h_idx, self.h_score)
+    pipeline._Readback.result = result_no_rows
+    run("no row read-back (second hop)")
+
+    # (b) additionally no first-hop copies (only the event)
+    def init_no_copies(self, out, d2h, after):
+        self.rt, self.idx, self.score = out
+        self.d2h = d2h
+        d2h.wait_event(after)
+        self.h_off = self.h_idx = self.h_score = torch.zeros(1)
+        self.h_tok = None
+        self.ev = torch.cuda.Event()
+        self.ev.record(d2h)
+    pipeline._Readback.__init__ = init_no_copies
+    run("no read-back copies at all")
+
+    # (c) and no host wait either: results are handed out without synchronising
+    def result_no_sync(self):
+        self._release()
+        return pipeline.HostResult(self.h_off, self.h_off, self.h_off, self.h_off)
+    pipeline._Readback.result = result_no_sync
+    run("... and no host sync")
+    pipeline._Readback.__init__, pipeline._Readback.result, pipeline._Readback._rows = orig_init, orig_result, orig_rows
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "variants2":
+    variants2()
+
+
+def variants3():
+    """Second hop of the read-back: is it the pinned allocation or the copy that opens the gap?"""
+    from setok_b200 import pipeline
+    dev = torch.device("cuda:0")
+    tok = bench.build_model(dev)
+    u8, imgs_h, noise_h = bench.host_batch(2, 0)
+    h_u8, h_noise = u8.pin_memory(), noise_h.pin_memory()
+    T = Timed(tok)
+    n = 14
+
+    def run(name):
+        for _ in stream_tokenize(T, ((h_u8, h_noise) for _ in range(n)), k=bench.KNN_K):
+            pass
+        T.report(name)
+
+    orig_rows = pipeline._Readback._rows
+    ring = [torch.empty(4096, 1024, dtype=torch.float32).pin_memory() for _ in range(3)]
+    state = {"i": 0}
+
+    def rows_prealloc(self, total):
+        buf = ring[state["i"] % 3][:total]
+        state["i"] += 1
+        buf.copy_(self.rt.data[:total], non_blocking=True)
+        return buf
+    pipeline._Readback._rows = rows_prealloc
+    run("rows into a preallocated ring")
+
+    def rows_alloc_only(self, total):
+        return torch.empty((total, self.rt.data.shape[1]), dtype=self.rt.data.dtype, pin_memory=True)
+    pipeline._Readback._rows = rows_alloc_only
+    run("pinned allocation, no copy")
+    pipeline._Readback._rows = orig_rows
+    run("as shipped")
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "variants3":
+    variants3()
+
+
+def hosttrace():
+    """Host-side timeline of stream_tokenize: when is each batch's launch sequence complete, when does each result come back?"""
+    import time
+    dev = torch.device("cuda:0")
+    tok = bench.build_model(dev)
+    u8, imgs_h, noise_h = bench.host_batch(2, 0)
+    h_u8, h_noise = u8.pin_memory(), noise_h.pin_memory()
+    launched, returned = [], []
+
+    class W:
+        device = tok.device
+
+        def __call__(self, *a, **k):
+            t0 = time.perf_counter()
+            out = tok(*a, **k)
+            launched.append((t0, time.perf_counter()))
+            return out
+    for rnd in range(2):
+        launched.clear(); returned.clear()
+        torch.cuda.synchronize()
+        for _ in stream_tokenize(W(), ((h_u8, h_noise) for _ in range(10)), k=bench.KNN_K):
+            returned.append(time.perf_counter())
+        base = launched[0][0]
+        for j in range(10):
+            print(f"round {rnd} batch {j}: launch begins {1e3 * (launched[j][0] - base):8.2f} ms, ends {1e3 * (launched[j][1] - base):8.2f} ms; "
+                  f"result returned {1e3 * (returned[j] - base):8.2f} ms", flush=True)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "hosttrace":
+    hosttrace()
