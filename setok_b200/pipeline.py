@@ -9,8 +9,9 @@
   i+1: its small header all-gather is enqueued right after batch i's kernels, the host reads that header -- and sizes /
   enqueues the row all-gather on the communication stream -- only after batch i+1 has been launched, so neither the host
   read nor the NCCL transfer ever idles the compute stream;
-* the D2H read-back of a finished batch's ragged result runs on its own stream (its row count is data-dependent, so
-  reading it needs a host sync -- which waits only for that batch, while the GPU runs the next ones).
+* the D2H read-back of a finished batch's ragged result runs on its own stream and is submitted right behind the batch's
+  kernels; its row count is data-dependent, so the rows are copied speculatively (the previous batch's count + 25 %) and only a
+  larger batch pays a second, host-issued hop.  The host sync waits only for that batch, while the GPU runs the next ones.
 
 Every batch is still copied in and its result copied out; nothing is cached across steps."""
 from __future__ import annotations
@@ -39,9 +40,10 @@ class HostResult:
 
 
 class _Readback:
-    """D2H of one batch's ragged result on a dedicated stream.  The row count is data-dependent, so the read-back is two
-    hops (offsets, then the packed rows) unless the host already knows the offsets (a gathered batch); both wait only for
-    THIS batch's kernels (an event), never for the batch the main stream is already running, and land in pinned memory.
+    """D2H of one batch's ragged result on a dedicated stream.  The row count is data-dependent: the host knows it either
+    already (a gathered batch), or from the offsets that come back with a speculatively sized copy of the rows (`guess_rows`),
+    or -- first batch, or a batch larger than the guess -- through a second hop.  Everything waits only for THIS batch's kernels
+    (an event), never for the batch the main stream is already running, and lands in pinned memory.
 
     The device tensors are kept alive by this object until `result()` has synchronised with the copies (no
     `Tensor.record_stream`: a recorded block is not reusable until the allocator has polled the side stream's event, which
