@@ -435,9 +435,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         uint2 rb[8];
         float4 rf[8];
         if (PF > 0) {
+          constexpr int PFm = PF > 0 ? PF : 1;      // (the branch is dead for PF == 0; keeps the modulo well-formed)
 #pragma unroll
-          for (int it = 0; it < 8; ++it) { if (RES == 1) rb[it] = rt[ch % PF][it]; else rf[it] = rtf[ch % PF][it]; }
-          if (PF < 4 && ch + PF < 4 && epi_mode == 0) prefetch(ch + PF, ch % PF);
+          for (int it = 0; it < 8; ++it) { if (RES == 1) rb[it] = rt[ch % PFm][it]; else rf[it] = rtf[ch % PFm][it]; }
+          if (PF < 4 && ch + PF < 4 && epi_mode == 0) prefetch(ch + PF, ch % PFm);
         } else if (res_kind == 1) {
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
