@@ -27,8 +27,9 @@ from .ragged import RaggedTokens
 class HostResult:
     """Host copy of one batch's output: packed tokens (sum K, C), offsets (B+1,), idx_cluster (B, N), score (B, 1, N)."""
 
-    def __init__(self, tokens, offsets, idx_cluster, score, copied_rows: Optional[int] = None):
+    def __init__(self, tokens, offsets, idx_cluster, score, copied_rows: Optional[int] = None, hops: int = 1):
         self.tokens, self.offsets, self.idx_cluster, self.score = tokens, offsets, idx_cluster, score
+        self.hops = hops                      # 2: the row count was not covered by the speculative copy (or there was none)
         # rows that actually crossed the bus (>= len(tokens) when the read-back was sized speculatively)
         self.copied_rows = int(tokens.shape[0]) if copied_rows is None else int(copied_rows)
 
@@ -88,6 +89,7 @@ class _Readback:
 
     def result(self) -> HostResult:
         self.ev.synchronize()
+        hops = 1
         if self.h_tok is None:
             total = int(self.h_off[-1])
             if self.h_guess is not None and total <= self.h_guess.shape[0]:
@@ -96,8 +98,9 @@ class _Readback:
                 with torch.cuda.stream(self.d2h):
                     self.h_tok = self._rows(total)
                 self.d2h.synchronize()
+                hops = 2
         self._release()
-        return HostResult(self.h_tok, self.h_off, self.h_idx, self.h_score, copied_rows=self.copied)
+        return HostResult(self.h_tok, self.h_off, self.h_idx, self.h_score, copied_rows=self.copied, hops=hops)
 
     def __del__(self):                                # abandoned before result(): the copies may still be reading the tensors
         try:

@@ -144,6 +144,34 @@ def test_stream_tokenize_matches_direct_forward():
         assert torch.equal(res.score, score.cpu()) and torch.equal(res.tokens, rt.data[:n].cpu())
 
 
+def test_stream_tokenize_speculative_readback_falls_back_when_a_batch_grows():
+    """The read-back copies the rows in ONE hop sized by an earlier batch's row count + 25 % (pipeline._Readback); a batch with
+    more rows than that must come back complete through the second hop, a smaller one as a prefix view -- both bit-equal to
+    the direct forward, and `copied_rows` accounts for every row that crossed the bus."""
+    from setok_b200.pipeline import stream_tokenize
+    C, L, H, P, IMG = 128, 2, 2, 4, 32
+    cfg = dict(hidden_size=C, intermediate_size=4 * C, num_hidden_layers=L, num_attention_heads=H, image_size=IMG, patch_size=P)
+    tok = _make_tokenizer(C, 64, 256, 8, 0.5, cfg, seed=4)
+    N = (IMG // P) ** 2
+    g = torch.Generator().manual_seed(19)
+    sizes = [2, 2, 2, 9, 9, 1, 1, 12]                    # image counts: the row count grows 4.5x, shrinks 9x, grows 12x
+    batches = [(torch.randn(b, 3, IMG, IMG, generator=g).pin_memory(), torch.rand(b, N, generator=g).pin_memory()) for b in sizes]
+    got = list(stream_tokenize(tok, iter(batches), k=8))
+    assert len(got) == len(batches)
+    second_hops = 0
+    for (imgs, noise), res in zip(batches, got):
+        rt, idx, score = tok(imgs.to(DEV), k=8, noise=noise.to(DEV))
+        n = int(rt.offsets[-1])
+        assert res.tokens.shape[0] == n and torch.equal(res.tokens, rt.data[:n].cpu())
+        assert torch.equal(res.offsets, rt.offsets.cpu()) and torch.equal(res.idx_cluster, idx.cpu()) and torch.equal(res.score, score.cpu())
+        assert res.copied_rows >= n and res.nbytes >= res.tokens.numel() * res.tokens.element_size()
+        second_hops += int(res.hops == 2)
+    # the guess of batch j comes from batch j - 2 (batch j - 1 is still in flight when j's read-back is set up): the first two
+    # batches have none (two hops), the batches that follow a 4.5x / 12x smaller one fall short of theirs, the others take one hop
+    hops = [r.hops for r in got]
+    assert hops[0] == 2 and hops[2] == 1 and hops[3] == 2 and hops[5] == 1 and hops[6] == 1 and hops[7] == 2, hops
+
+
 def test_head_golden():
     """Head golden (C=64): clustering bit-exact, group features and tokens within bf16-GEMM tolerance."""
     g = load_golden("head")
