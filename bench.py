@@ -653,6 +653,7 @@ def run_config3(args):
     pk = peaks()
     counts = (last["rt"].offsets[1:] - last["rt"].offsets[:-1]).float()
     tok_ms = cuda_time(lambda: tok(images, k=KNN_K, noise=noise), 3)
+    vit_ms = cuda_time(lambda: tok.image_feature_encoder(images), 3)
     rt = last["rt"]
     det_ms = cuda_time(lambda: det(rt), 3)
     gemm_ms, gemm_flops, gemm_tf = time_gemm_mix(dev, layers_run, B * 577, reps=1)
@@ -671,7 +672,11 @@ def run_config3(args):
             "roofline": {"kernel": "gemm_bf16_tcgen05_kernel (ViT layer launch mix at M = 128 x 577 rows)", "bound": "tensor", "achieved": gemm_tf,
                          "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": gemm_tf / pk["tf_sustained"], "traffic": None,
                          "flops_per_launch": gemm_flops, "ms_per_launch": gemm_ms, "peak_source": f"{pk['src']} sustained bf16",
-                         "whole_step_tensor_frac": (flops / (step_ms * 1e-3) / 1e12) / pk["tf_sustained"], "whole_step_flops": flops}}
+                         "whole_step_tensor_frac": (flops / (step_ms * 1e-3) / 1e12) / pk["tf_sustained"], "whole_step_flops": flops},
+            "roofline_vit": {"kernel": "whole ViT-L/14 tower at 336^2 (T = 577; chunked tcgen05 attention)", "bound": "tensor", "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                             "achieved": B * vit_flops_per_image(layers_run, 336) / (vit_ms * 1e-3) / 1e12,
+                             "frac": (B * vit_flops_per_image(layers_run, 336) / (vit_ms * 1e-3) / 1e12) / pk["tf_sustained"], "ms": vit_ms,
+                             "flops": B * vit_flops_per_image(layers_run, 336)}}
     if world == 1 and not args.no_cpu:
         orc = CpuOracle(3, 1)
         secs, st = orc.run(1)
